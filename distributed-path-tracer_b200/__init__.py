@@ -1,0 +1,542 @@
+"""distributed-path-tracer_b200 — B200-native hot path of vmanam0451/distributed-path-tracer.
+
+The product is ``libptb.so`` (C ABI in ``include/ptb.h``: sm_100a wavefront kernels for KD-tree
+traversal, ray/triangle intersection and the Monte-Carlo integrator).  This package is the
+thin host-side mirror of the reference's public interface for that path:
+
+* :class:`Renderer` mirrors ``core::renderer`` (``path_tracer_lib/path_tracer/core/renderer.hpp:15-36``):
+  the same public fields (``resolution``, ``sample_count``, ``bounce_count``, ``camera_index``,
+  ``sun_light_index``, ``environment_factor``, ``transparent_background``), ``load_gltf`` and ``render``.
+* :func:`worker_render` mirrors the Lambda worker's request (``src/models/work_info.hpp:17-31``:
+  ``samples, bounces, X, Y``) with the tile / seed extensions.
+
+There is no CPU fallback: importing works anywhere, but every compute call raises
+:class:`PtbError` when ``libptb.so`` is missing or no CUDA device is usable.
+The directory name is not a Python identifier; import it with
+``importlib.import_module("distributed-path-tracer_b200")`` or through the ``ptb200`` shim at the repo root.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libptb.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "ptb.h")
+
+PTB_OK, PTB_E_INVALID, PTB_E_CUDA, PTB_E_NCCL, PTB_E_OOM, PTB_E_IO = range(6)
+NO_TEXTURE = 0xFFFFFFFF
+MISS = 0xFFFFFFFF
+NO_SUN_LIGHT = 0xFFFFFFFF
+INTEGRATOR_LIB, INTEGRATOR_APP_RR = 0, 1
+
+u32p = C.POINTER(C.c_uint32)
+f32p = C.POINTER(C.c_float)
+
+
+class PtbError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"ptb status {status}: {message}")
+        self.status = status
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("positions", f32p), ("normals", f32p), ("tangents", f32p), ("uvs", f32p),
+                ("n_vertices", C.c_uint32), ("indices", u32p), ("n_triangles", C.c_uint32)]
+
+
+class SurfaceDesc(C.Structure):
+    _fields_ = [("mesh", C.c_uint32), ("material", C.c_uint32)]
+
+
+class InstanceDesc(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("basis", C.c_float * 9),
+                ("first_surface", C.c_uint32), ("n_surfaces", C.c_uint32)]
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("channels", C.c_uint32), ("is_float", C.c_uint32), ("srgb", C.c_uint32)]
+
+
+class MaterialDesc(C.Structure):
+    _fields_ = [("albedo", C.c_float * 3), ("opacity", C.c_float), ("roughness", C.c_float),
+                ("metallic", C.c_float), ("emissive", C.c_float * 3), ("ior", C.c_float),
+                ("shadow_catcher", C.c_uint32),
+                ("normal_tex", C.c_uint32), ("albedo_tex", C.c_uint32), ("opacity_tex", C.c_uint32),
+                ("roughness_tex", C.c_uint32), ("metallic_tex", C.c_uint32), ("emissive_tex", C.c_uint32)]
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("basis", C.c_float * 9), ("yfov", C.c_float)]
+
+
+class SunDesc(C.Structure):
+    _fields_ = [("enabled", C.c_uint32), ("basis", C.c_float * 9), ("energy", C.c_float * 3),
+                ("angular_radius", C.c_float)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("meshes", C.POINTER(MeshDesc)), ("n_meshes", C.c_uint32),
+                ("surfaces", C.POINTER(SurfaceDesc)), ("n_surfaces", C.c_uint32),
+                ("instances", C.POINTER(InstanceDesc)), ("n_instances", C.c_uint32),
+                ("materials", C.POINTER(MaterialDesc)), ("n_materials", C.c_uint32),
+                ("textures", C.POINTER(TextureDesc)), ("n_textures", C.c_uint32),
+                ("camera", CameraDesc), ("sun", SunDesc),
+                ("environment_factor", C.c_float * 3), ("transparent_background", C.c_uint32),
+                ("kd_use_sah", C.c_uint32), ("kd_max_depth", C.c_uint32)]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("n_instances", C.c_uint32), ("n_surfaces", C.c_uint32), ("n_meshes", C.c_uint32),
+                ("n_materials", C.c_uint32), ("n_textures", C.c_uint32),
+                ("n_triangles", C.c_uint64), ("n_kd_nodes", C.c_uint64), ("n_kd_branches", C.c_uint64),
+                ("n_kd_leaves", C.c_uint64), ("n_leaf_refs", C.c_uint64),
+                ("kd_max_depth_reached", C.c_uint32), ("device_bytes", C.c_uint64),
+                ("build_seconds", C.c_double), ("upload_seconds", C.c_double)]
+
+
+class TileReq(C.Structure):
+    _fields_ = [("full_w", C.c_uint32), ("full_h", C.c_uint32), ("x0", C.c_uint32), ("y0", C.c_uint32),
+                ("w", C.c_uint32), ("h", C.c_uint32), ("spp", C.c_uint32), ("max_depth", C.c_uint32),
+                ("seed", C.c_uint64), ("first_sample", C.c_uint32), ("integrator", C.c_uint32),
+                ("first_sample_unjittered", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("gpu_seconds", C.c_double), ("extend_seconds", C.c_double), ("shade_seconds", C.c_double),
+                ("extend_launches", C.c_uint64), ("node_visits", C.c_uint64), ("leaf_visits", C.c_uint64),
+                ("tri_tests", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+HIT_DTYPE = np.dtype([("instance", "<u4"), ("surface", "<u4"), ("triangle", "<u4"),
+                      ("t", "<f4"), ("bary", "<f4", (3,))])
+
+# Every symbol include/ptb.h declares (checked against the header by tests/test_abi.py).
+EXPORTS = [
+    "ptb_scene_create", "ptb_scene_load_gltf", "ptb_scene_destroy", "ptb_scene_get_info", "ptb_scene_dump_kd",
+    "ptb_trace_rays", "ptb_trace_rays_attrs", "ptb_render_tile", "ptb_render_tile_dev", "ptb_tonemap_rgba8",
+    "ptb_write_png", "ptb_host_build_kd", "ptb_desc_load_gltf", "ptb_desc_get", "ptb_desc_free",
+    "ptb_camera_rays", "ptb_trace_rays_stats", "ptb_extend_registers", "ptb_set_option", "ptb_last_error",
+    "ptb_abi_version", "ptb_device_count",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libptb.so.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise PtbError(PTB_E_CUDA, f"{SO_PATH} is missing — run `python distributed-path-tracer_b200/build.py` "
+                                   "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(SO_PATH)
+    st = C.c_int
+    L.ptb_scene_create.restype = st
+    L.ptb_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.c_void_p)]
+    L.ptb_scene_load_gltf.restype = st
+    L.ptb_scene_load_gltf.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+    L.ptb_scene_destroy.restype = None
+    L.ptb_scene_destroy.argtypes = [C.c_void_p]
+    L.ptb_scene_get_info.restype = st
+    L.ptb_scene_get_info.argtypes = [C.c_void_p, C.POINTER(SceneInfo)]
+    L.ptb_scene_dump_kd.restype = st
+    L.ptb_scene_dump_kd.argtypes = [C.c_void_p, C.c_uint32, u32p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.ptb_trace_rays.restype = st
+    L.ptb_trace_rays.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_void_p]
+    L.ptb_trace_rays_attrs.restype = st
+    L.ptb_trace_rays_attrs.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_void_p, f32p]
+    L.ptb_trace_rays_stats.restype = st
+    L.ptb_trace_rays_stats.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_void_p, C.POINTER(RenderStats)]
+    L.ptb_camera_rays.restype = st
+    L.ptb_camera_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, u32p, u32p, f32p, C.c_uint64, f32p]
+    L.ptb_render_tile.restype = st
+    L.ptb_render_tile.argtypes = [C.c_void_p, C.POINTER(TileReq), f32p, f32p, C.POINTER(RenderStats)]
+    L.ptb_render_tile_dev.restype = st
+    L.ptb_render_tile_dev.argtypes = [C.c_void_p, C.POINTER(TileReq), C.c_void_p, C.c_void_p,
+                                      C.POINTER(RenderStats)]
+    L.ptb_tonemap_rgba8.restype = st
+    L.ptb_tonemap_rgba8.argtypes = [f32p, f32p, C.c_uint64, C.c_void_p]
+    L.ptb_write_png.restype = st
+    L.ptb_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.ptb_host_build_kd.restype = st
+    L.ptb_host_build_kd.argtypes = [f32p, C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                    u32p, C.c_uint64, C.POINTER(C.c_uint64), f32p]
+    L.ptb_desc_load_gltf.restype = st
+    L.ptb_desc_load_gltf.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.ptb_desc_get.restype = C.POINTER(SceneDesc)
+    L.ptb_desc_get.argtypes = [C.c_void_p]
+    L.ptb_desc_free.restype = None
+    L.ptb_desc_free.argtypes = [C.c_void_p]
+    L.ptb_set_option.restype = st
+    L.ptb_set_option.argtypes = [C.c_char_p, C.c_int64]
+    L.ptb_last_error.restype = C.c_char_p
+    L.ptb_abi_version.restype = C.c_int
+    L.ptb_device_count.restype = C.c_int
+    L.ptb_extend_registers.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(status: int):
+    if status != PTB_OK:
+        raise PtbError(status, lib().ptb_last_error().decode("utf-8", "replace"))
+
+
+def _fp(a):
+    return a.ctypes.data_as(f32p)
+
+
+def _up(a):
+    return a.ctypes.data_as(u32p)
+
+
+def set_option(name: str, value: int):
+    _check(lib().ptb_set_option(name.encode(), int(value)))
+
+
+def device_count() -> int:
+    return lib().ptb_device_count()
+
+
+class SceneDescription:
+    """A flat scene description (the kept "scene, camera and material API" of the reference, as arrays).
+
+    meshes:    list of dict(positions[nv,3], normals[nv,3], tangents[nv,3], uvs[nv,2], indices[nt,3])
+    surfaces:  uint32[ns,2] = (mesh, material)              -- scene::model::surface
+    instances: list of (origin[3], basis[9], first_surface, n_surfaces), in renderer::intersect visiting order
+    materials: list of dict(albedo, opacity, roughness, metallic, emissive, ior, shadow_catcher, *_tex)
+    camera:    (origin[3], basis[9], yfov);  sun: None | (basis[9], energy[3], angular_radius)
+    textures:  list of dict(pixels ndarray[h,w,c] uint8|float32, srgb)
+    """
+
+    def __init__(self, meshes, surfaces, instances, materials, camera, sun=None,
+                 environment_factor=(1.0, 1.0, 1.0), transparent_background=False,
+                 kd_use_sah=True, kd_max_depth=25, textures=()):
+        self.meshes = [
+            {k: np.ascontiguousarray(m[k], dtype=np.uint32 if k == "indices" else np.float32)
+             for k in ("positions", "normals", "tangents", "uvs", "indices")} for m in meshes]
+        self.surfaces = np.ascontiguousarray(surfaces, dtype=np.uint32).reshape(-1, 2)
+        self.instances = [(np.asarray(o, np.float32), np.asarray(b, np.float32), int(f), int(c))
+                          for (o, b, f, c) in instances]
+        self.materials = [dict(m) for m in materials]
+        self.camera = (np.asarray(camera[0], np.float32), np.asarray(camera[1], np.float32), float(camera[2]))
+        self.sun = sun
+        self.environment_factor = tuple(float(x) for x in environment_factor)
+        self.transparent_background = bool(transparent_background)
+        self.kd_use_sah = bool(kd_use_sah)
+        self.kd_max_depth = int(kd_max_depth)
+        self.textures = list(textures)
+
+    @property
+    def n_triangles(self) -> int:
+        return sum(len(m["indices"]) for m in self.meshes)
+
+    def to_c(self):
+        keep = []
+        md = (MeshDesc * max(1, len(self.meshes)))()
+        for i, m in enumerate(self.meshes):
+            md[i].positions, md[i].normals = _fp(m["positions"]), _fp(m["normals"])
+            md[i].tangents, md[i].uvs = _fp(m["tangents"]), _fp(m["uvs"])
+            md[i].n_vertices = len(m["positions"])
+            md[i].indices = _up(m["indices"])
+            md[i].n_triangles = len(m["indices"])
+        sd = (SurfaceDesc * max(1, len(self.surfaces)))()
+        for i, (me, ma) in enumerate(self.surfaces):
+            sd[i].mesh, sd[i].material = int(me), int(ma)
+        idesc = (InstanceDesc * max(1, len(self.instances)))()
+        for i, (o, b, f, c) in enumerate(self.instances):
+            idesc[i].origin[:] = [float(x) for x in o]
+            idesc[i].basis[:] = [float(x) for x in b]
+            idesc[i].first_surface, idesc[i].n_surfaces = f, c
+        mat = (MaterialDesc * max(1, len(self.materials)))()
+        for i, m in enumerate(self.materials):
+            mat[i].albedo[:] = [float(x) for x in m.get("albedo", (1, 1, 1))]
+            mat[i].opacity = float(m.get("opacity", 1.0))
+            mat[i].roughness = float(m.get("roughness", 1.0))
+            mat[i].metallic = float(m.get("metallic", 1.0))
+            mat[i].emissive[:] = [float(x) for x in m.get("emissive", (0, 0, 0))]
+            mat[i].ior = float(m.get("ior", 1.33))
+            mat[i].shadow_catcher = int(m.get("shadow_catcher", 0))
+            for slot in ("normal", "albedo", "opacity", "roughness", "metallic", "emissive"):
+                setattr(mat[i], slot + "_tex", int(m.get(slot + "_tex", NO_TEXTURE)))
+        tex = (TextureDesc * max(1, len(self.textures)))()
+        for i, t in enumerate(self.textures):
+            px = np.ascontiguousarray(t["pixels"])
+            keep.append(px)
+            tex[i].pixels = px.ctypes.data
+            tex[i].height, tex[i].width = px.shape[0], px.shape[1]
+            tex[i].channels = px.shape[2] if px.ndim == 3 else 1
+            tex[i].is_float = 1 if px.dtype == np.float32 else 0
+            tex[i].srgb = int(bool(t.get("srgb", False)))
+        d = SceneDesc()
+        d.meshes, d.n_meshes = md, len(self.meshes)
+        d.surfaces, d.n_surfaces = sd, len(self.surfaces)
+        d.instances, d.n_instances = idesc, len(self.instances)
+        d.materials, d.n_materials = mat, len(self.materials)
+        d.textures, d.n_textures = tex, len(self.textures)
+        d.camera.origin[:] = [float(x) for x in self.camera[0]]
+        d.camera.basis[:] = [float(x) for x in self.camera[1]]
+        d.camera.yfov = self.camera[2]
+        if self.sun is not None:
+            d.sun.enabled = 1
+            d.sun.basis[:] = [float(x) for x in self.sun[0]]
+            d.sun.energy[:] = [float(x) for x in self.sun[1]]
+            d.sun.angular_radius = float(self.sun[2])
+        d.environment_factor[:] = list(self.environment_factor)
+        d.transparent_background = int(self.transparent_background)
+        d.kd_use_sah = int(self.kd_use_sah)
+        d.kd_max_depth = self.kd_max_depth
+        keep += [md, sd, idesc, mat, tex, self]
+        return d, keep
+
+    @classmethod
+    def from_c(cls, d: SceneDesc) -> "SceneDescription":
+        """Deep copy of a C description (e.g. what ptb_desc_load_gltf produced)."""
+        def arr(ptr, n, dtype, shape):
+            if n == 0:
+                return np.zeros(shape, dtype)
+            return np.ctypeslib.as_array(ptr, shape=(int(np.prod(shape)),)).astype(dtype).reshape(shape).copy()
+        meshes = []
+        for i in range(d.n_meshes):
+            m = d.meshes[i]
+            nv, nt = m.n_vertices, m.n_triangles
+            meshes.append(dict(positions=arr(m.positions, nv, np.float32, (nv, 3)),
+                               normals=arr(m.normals, nv, np.float32, (nv, 3)),
+                               tangents=arr(m.tangents, nv, np.float32, (nv, 3)),
+                               uvs=arr(m.uvs, nv, np.float32, (nv, 2)),
+                               indices=arr(m.indices, nt, np.uint32, (nt, 3))))
+        surfaces = np.array([(d.surfaces[i].mesh, d.surfaces[i].material) for i in range(d.n_surfaces)],
+                            np.uint32).reshape(-1, 2)
+        instances = [(list(d.instances[i].origin), list(d.instances[i].basis), d.instances[i].first_surface,
+                      d.instances[i].n_surfaces) for i in range(d.n_instances)]
+        materials = []
+        for i in range(d.n_materials):
+            m = d.materials[i]
+            materials.append(dict(albedo=tuple(m.albedo), opacity=m.opacity, roughness=m.roughness,
+                                  metallic=m.metallic, emissive=tuple(m.emissive), ior=m.ior,
+                                  shadow_catcher=m.shadow_catcher, normal_tex=m.normal_tex,
+                                  albedo_tex=m.albedo_tex, opacity_tex=m.opacity_tex,
+                                  roughness_tex=m.roughness_tex, metallic_tex=m.metallic_tex,
+                                  emissive_tex=m.emissive_tex))
+        textures = []
+        for i in range(d.n_textures):
+            t = d.textures[i]
+            n = t.width * t.height * t.channels
+            if t.is_float:
+                px = np.ctypeslib.as_array(C.cast(t.pixels, f32p), shape=(n,)).copy()
+            else:
+                px = np.ctypeslib.as_array(C.cast(t.pixels, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+            textures.append(dict(pixels=px.reshape(t.height, t.width, t.channels), srgb=bool(t.srgb)))
+        sun = (list(d.sun.basis), list(d.sun.energy), d.sun.angular_radius) if d.sun.enabled else None
+        return cls(meshes, surfaces, instances, materials,
+                   (list(d.camera.origin), list(d.camera.basis), d.camera.yfov), sun,
+                   tuple(d.environment_factor), bool(d.transparent_background),
+                   bool(d.kd_use_sah), d.kd_max_depth or 25, textures)
+
+
+def load_gltf_description(path, camera_index=0, sun_light_index=0) -> SceneDescription:
+    """Host-only half of renderer::load_gltf: parse a glTF file into a description (no GPU needed)."""
+    h = C.c_void_p()
+    _check(lib().ptb_desc_load_gltf(os.fsencode(path), camera_index, sun_light_index, C.byref(h)))
+    try:
+        return SceneDescription.from_c(lib().ptb_desc_get(h).contents)
+    finally:
+        lib().ptb_desc_free(h)
+
+
+def host_build_kd(positions, indices, use_sah=True, max_depth=25, threads=0):
+    """Host-only KD build of one mesh → (record stream as ptb_scene_dump_kd, aabb[6]). No GPU needed."""
+    pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+    n = C.c_uint64()
+    aabb = np.zeros(6, np.float32)
+    # one build to learn the size would double the cost; 16 words per triangle + slack always suffices
+    # for the reference's SAH (≤ ~14x duplication measured); fall back to the exact two-pass otherwise.
+    cap = max(1024, len(idx) * 24 + 1024)
+    words = np.empty(cap, np.uint32)
+    st = lib().ptb_host_build_kd(_fp(pos), len(pos), _up(idx), len(idx), int(use_sah), max_depth, threads,
+                                 _up(words), cap, C.byref(n), _fp(aabb))
+    if st != PTB_OK and n.value > cap:
+        words = np.empty(n.value, np.uint32)
+        st = lib().ptb_host_build_kd(_fp(pos), len(pos), _up(idx), len(idx), int(use_sah), max_depth, threads,
+                                     _up(words), n.value, C.byref(n), _fp(aabb))
+    _check(st)
+    return words[:n.value].copy(), aabb
+
+
+class Scene:
+    """A scene resident in HBM (ptb_scene)."""
+
+    def __init__(self, handle, keep=None):
+        self.h = handle
+        self._keep = keep
+
+    @classmethod
+    def create(cls, desc: SceneDescription, device: int = 0) -> "Scene":
+        d, keep = desc.to_c()
+        h = C.c_void_p()
+        _check(lib().ptb_scene_create(C.byref(d), device, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load_gltf(cls, path, camera_index=0, sun_light_index=0, device=0) -> "Scene":
+        h = C.c_void_p()
+        _check(lib().ptb_scene_load_gltf(os.fsencode(path), camera_index, sun_light_index, device, C.byref(h)))
+        return cls(h)
+
+    def close(self):
+        if self.h:
+            lib().ptb_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def info(self) -> dict:
+        i = SceneInfo()
+        _check(lib().ptb_scene_get_info(self.h, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in i._fields_}
+
+    def dump_kd(self, mesh: int) -> np.ndarray:
+        n = C.c_uint64()
+        _check(lib().ptb_scene_dump_kd(self.h, mesh, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.uint32)
+        _check(lib().ptb_scene_dump_kd(self.h, mesh, _up(out), n.value, C.byref(n)))
+        return out
+
+    def trace_rays(self, origin_dir, attrs=False, stats=False):
+        od = np.ascontiguousarray(origin_dir, np.float32).reshape(-1, 6)
+        hits = np.zeros(len(od), HIT_DTYPE)
+        if stats:
+            s = RenderStats()
+            _check(lib().ptb_trace_rays_stats(self.h, _fp(od), len(od), hits.ctypes.data, C.byref(s)))
+            return hits, s.as_dict()
+        if attrs:
+            at = np.zeros((len(od), 14), np.float32)
+            _check(lib().ptb_trace_rays_attrs(self.h, _fp(od), len(od), hits.ctypes.data, _fp(at)))
+            return hits, at
+        _check(lib().ptb_trace_rays(self.h, _fp(od), len(od), hits.ctypes.data))
+        return hits
+
+    def camera_rays(self, w, h, px, py, aa):
+        px = np.ascontiguousarray(px, np.uint32)
+        py = np.ascontiguousarray(py, np.uint32)
+        aa = np.ascontiguousarray(aa, np.float32).reshape(-1, 2)
+        od = np.empty((len(px), 6), np.float32)
+        _check(lib().ptb_camera_rays(self.h, w, h, _up(px), _up(py), _fp(aa), len(px), _fp(od)))
+        return od
+
+    @staticmethod
+    def _req(full_w, full_h, spp, max_depth, tile, seed, integrator, first_sample, first_sample_unjittered):
+        x0, y0, w, h = tile if tile else (0, 0, full_w, full_h)
+        return TileReq(full_w, full_h, x0, y0, w, h, spp, max_depth, seed, first_sample, integrator,
+                       int(first_sample_unjittered), 0)
+
+    def render_tile(self, full_w, full_h, spp, max_depth, tile=None, seed=1, integrator=INTEGRATOR_LIB,
+                    first_sample=0, first_sample_unjittered=False):
+        """→ (rgb[h,w,3] linear running mean, alpha[h,w], stats dict); host buffers, synchronous."""
+        req = self._req(full_w, full_h, spp, max_depth, tile, seed, integrator, first_sample,
+                        first_sample_unjittered)
+        rgb = np.empty((req.h, req.w, 3), np.float32)
+        alpha = np.empty((req.h, req.w), np.float32)
+        s = RenderStats()
+        _check(lib().ptb_render_tile(self.h, C.byref(req), _fp(rgb), _fp(alpha), C.byref(s)))
+        return rgb, alpha, s.as_dict()
+
+    def render_tile_dev(self, rgba_dev_ptr: int, full_w, full_h, spp, max_depth, tile=None, seed=1,
+                        integrator=INTEGRATOR_LIB, first_sample=0, first_sample_unjittered=False, stream=0,
+                        want_stats=True):
+        """Result stays in device memory (w*h float4 at rgba_dev_ptr); stream is a cudaStream_t value."""
+        req = self._req(full_w, full_h, spp, max_depth, tile, seed, integrator, first_sample,
+                        first_sample_unjittered)
+        s = RenderStats()
+        _check(lib().ptb_render_tile_dev(self.h, C.byref(req), C.c_void_p(rgba_dev_ptr), C.c_void_p(stream),
+                                         C.byref(s) if want_stats else None))
+        return s.as_dict() if want_stats else None
+
+
+def tonemap_rgba8(rgb, alpha=None) -> np.ndarray:
+    """tonemap_approx_aces + sRGB encode + RGBA8 (core/utils.hpp:29-36, image/image.cpp:143-154), on the GPU."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    shape = rgb.shape[:-1]
+    flat = rgb.reshape(-1, 3)
+    a = np.ascontiguousarray(alpha, np.float32).reshape(-1) if alpha is not None else None
+    out = np.empty((len(flat), 4), np.uint8)
+    _check(lib().ptb_tonemap_rgba8(_fp(flat), _fp(a) if a is not None else None, len(flat), out.ctypes.data))
+    return out.reshape(*shape, 4)
+
+
+def write_png(path, rgba8):
+    rgba8 = np.ascontiguousarray(rgba8, np.uint8)
+    h, w = rgba8.shape[:2]
+    _check(lib().ptb_write_png(os.fsencode(path), rgba8.ctypes.data, w, h))
+
+
+class Renderer:
+    """Mirror of ``core::renderer`` (reference ``core/renderer.hpp:15-36``): same fields, same two calls."""
+
+    no_sun_light = NO_SUN_LIGHT
+
+    def __init__(self, device: int = 0):
+        self.resolution = (1920, 1080)     # renderer.hpp:21
+        self.thread_count = 0              # kept for interface parity; the GPU grid replaces the pool
+        self.sample_count = 10000          # :23
+        self.bounce_count = 4              # :24
+        self.environment_factor = (1.0, 1.0, 1.0)
+        self.transparent_background = False
+        self.camera_index = 0
+        self.sun_light_index = 0
+        self.seed = 1                      # extension: the reference RNG is unseeded
+        self.integrator = INTEGRATOR_LIB
+        self.device = device
+        self.scene: Scene | None = None
+        self.last_stats: dict | None = None
+
+    def load_gltf(self, path):
+        desc = load_gltf_description(path, self.camera_index, self.sun_light_index)
+        desc.environment_factor = tuple(self.environment_factor)
+        desc.transparent_background = bool(self.transparent_background)
+        self.scene = Scene.create(desc, self.device)
+
+    def load_description(self, desc: SceneDescription):
+        self.scene = Scene.create(desc, self.device)
+
+    def render_linear(self):
+        if self.scene is None:
+            raise PtbError(PTB_E_INVALID, "Scene is missing a camera.")  # renderer.cpp:97-98
+        w, h = self.resolution
+        rgb, alpha, st = self.scene.render_tile(w, h, self.sample_count, self.bounce_count, seed=self.seed,
+                                                integrator=self.integrator)
+        self.last_stats = st
+        return rgb, alpha
+
+    def render(self) -> np.ndarray:
+        """→ RGBA8 image [h,w,4], what the reference encodes into its PNG."""
+        rgb, alpha = self.render_linear()
+        return tonemap_rgba8(rgb, alpha)
+
+
+def worker_render(scene: Scene, samples: int, bounces: int, X: int, Y: int, tile=None, seed=1,
+                  integrator=INTEGRATOR_APP_RR, first_sample_unjittered=True):
+    """The Lambda worker's request (``worker_info``: samples, bounces, X, Y) → RGBA8 [h,w,4] + stats."""
+    rgb, alpha, st = scene.render_tile(int(X), int(Y), int(samples), int(bounces), tile=tile, seed=seed,
+                                       integrator=integrator, first_sample_unjittered=first_sample_unjittered)
+    return tonemap_rgba8(rgb, alpha), st

@@ -1,0 +1,225 @@
+// api.cu — the extern "C" boundary declared in include/ptb.h.  Catches every
+// exception, maps it to a ptb_status and a thread-local message.
+
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "errors.hpp"
+#include "kd_build.hpp"
+#include "kernels.hpp"
+#include "render.hpp"
+#include "scene.hpp"
+
+namespace {
+
+thread_local std::string tl_error;
+
+template <typename F>
+ptb_status guarded(F&& f) {
+    try {
+        f();
+        tl_error.clear();
+        return PTB_OK;
+    } catch (const ptb::Error& e) {
+        tl_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        tl_error = "host allocation failed";
+        return PTB_E_OOM;
+    } catch (const std::exception& e) {
+        tl_error = e.what();
+        return PTB_E_INVALID;
+    } catch (...) {
+        tl_error = "unknown error";
+        return PTB_E_INVALID;
+    }
+}
+
+} // namespace
+
+struct ptb_desc {
+    ptb::OwnedScene owned;
+    ptb_scene_desc view;
+};
+
+extern "C" {
+
+ptb_status ptb_scene_create(const ptb_scene_desc* desc, int device, ptb_scene** out) {
+    return guarded([&] {
+        if (!desc || !out) throw ptb::Error(PTB_E_INVALID, "desc or out is NULL");
+        *out = nullptr;
+        *out = ptb::create_scene(*desc, device);
+    });
+}
+
+ptb_status ptb_scene_load_gltf(const char* path, uint32_t camera_index, uint32_t sun_light_index, int device,
+                               ptb_scene** out) {
+    return guarded([&] {
+        if (!path || !out) throw ptb::Error(PTB_E_INVALID, "path or out is NULL");
+        *out = nullptr;
+        ptb::OwnedScene owned;
+        ptb::load_gltf(path, camera_index, sun_light_index, owned);
+        *out = ptb::create_scene(owned.view(), device);
+    });
+}
+
+void ptb_scene_destroy(ptb_scene* scene) {
+    try {
+        ptb::destroy_scene(scene);
+    } catch (...) {
+    }
+}
+
+ptb_status ptb_scene_get_info(const ptb_scene* scene, ptb_scene_info* out) {
+    return guarded([&] {
+        if (!scene || !out) throw ptb::Error(PTB_E_INVALID, "scene or out is NULL");
+        *out = scene->info;
+    });
+}
+
+ptb_status ptb_scene_dump_kd(const ptb_scene* scene, uint32_t mesh, uint32_t* words, uint64_t capacity,
+                             uint64_t* n_words) {
+    return guarded([&] {
+        if (!scene || !n_words) throw ptb::Error(PTB_E_INVALID, "scene or n_words is NULL");
+        if (mesh >= scene->trees.size()) throw ptb::Error(PTB_E_INVALID, "mesh out of range");
+        std::vector<uint32_t> w;
+        ptb::dump_kd_tree(scene->trees[mesh], w);
+        *n_words = w.size();
+        if (words) {
+            if (capacity < w.size()) throw ptb::Error(PTB_E_INVALID, "capacity too small");
+            std::memcpy(words, w.data(), w.size() * sizeof(uint32_t));
+        }
+    });
+}
+
+// Host-only twin of the build step of ptb_scene_create, for tests that have no GPU.
+ptb_status ptb_host_build_kd(const float* positions, uint32_t n_vertices, const uint32_t* indices,
+                             uint32_t n_triangles, uint32_t use_sah, uint32_t max_depth, int threads, uint32_t* words,
+                             uint64_t capacity, uint64_t* n_words, float* aabb6_out) {
+    return guarded([&] {
+        if (!n_words) throw ptb::Error(PTB_E_INVALID, "n_words is NULL");
+        if ((n_vertices && !positions) || (n_triangles && !indices)) throw ptb::Error(PTB_E_INVALID, "NULL input");
+        for (size_t i = 0; i < size_t(n_triangles) * 3; i++)
+            if (indices[i] >= n_vertices) throw ptb::Error(PTB_E_INVALID, "triangle index out of range");
+        if (max_depth == 0) max_depth = 25;
+        const ptb::Aabb box = ptb::mesh_aabb(positions, n_vertices);
+        if (aabb6_out) {
+            for (int a = 0; a < 3; a++) {
+                aabb6_out[a] = box.min[a];
+                aabb6_out[3 + a] = box.max[a];
+            }
+        }
+        ptb::KdTree tree;
+        ptb::build_kd_tree(positions, indices, n_triangles, box, use_sah != 0, max_depth, threads, tree);
+        std::vector<uint32_t> w;
+        ptb::dump_kd_tree(tree, w);
+        *n_words = w.size();
+        if (words) {
+            if (capacity < w.size()) throw ptb::Error(PTB_E_INVALID, "capacity too small");
+            std::memcpy(words, w.data(), w.size() * sizeof(uint32_t));
+        }
+    });
+}
+
+// Host-only: parse a glTF file into a scene description without touching CUDA.
+ptb_status ptb_desc_load_gltf(const char* path, uint32_t camera_index, uint32_t sun_light_index, ptb_desc** out) {
+    return guarded([&] {
+        if (!path || !out) throw ptb::Error(PTB_E_INVALID, "path or out is NULL");
+        *out = nullptr;
+        auto* d = new ptb_desc;
+        try {
+            ptb::load_gltf(path, camera_index, sun_light_index, d->owned);
+            d->view = d->owned.view();
+        } catch (...) {
+            delete d;
+            throw;
+        }
+        *out = d;
+    });
+}
+
+const ptb_scene_desc* ptb_desc_get(const ptb_desc* d) { return d ? &d->view : nullptr; }
+
+void ptb_desc_free(ptb_desc* d) { delete d; }
+
+ptb_status ptb_trace_rays(const ptb_scene* scene, const float* origin_dir, uint64_t n, ptb_hit* hits_out) {
+    return guarded([&] { ptb::trace_rays_host(scene, origin_dir, n, hits_out, nullptr, nullptr); });
+}
+
+ptb_status ptb_trace_rays_attrs(const ptb_scene* scene, const float* origin_dir, uint64_t n, ptb_hit* hits_out,
+                                float* attrs_out) {
+    return guarded([&] { ptb::trace_rays_host(scene, origin_dir, n, hits_out, attrs_out, nullptr); });
+}
+
+ptb_status ptb_trace_rays_stats(const ptb_scene* scene, const float* origin_dir, uint64_t n, ptb_hit* hits_out,
+                                ptb_render_stats* stats_out) {
+    return guarded([&] { ptb::trace_rays_host(scene, origin_dir, n, hits_out, nullptr, stats_out); });
+}
+
+ptb_status ptb_camera_rays(const ptb_scene* scene, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py,
+                           const float* aa, uint64_t n, float* origin_dir_out) {
+    return guarded([&] {
+        if (n && (!px || !py || !aa || !origin_dir_out)) throw ptb::Error(PTB_E_INVALID, "NULL argument");
+        ptb::camera_rays_host(scene, w, h, px, py, aa, n, origin_dir_out);
+    });
+}
+
+ptb_status ptb_render_tile(const ptb_scene* scene, const ptb_tile_req* req, float* rgb_out, float* alpha_out,
+                           ptb_render_stats* stats_out) {
+    return guarded([&] {
+        if (!req) throw ptb::Error(PTB_E_INVALID, "req is NULL");
+        ptb::render_tile_host(scene, *req, rgb_out, alpha_out, stats_out);
+    });
+}
+
+ptb_status ptb_render_tile_dev(const ptb_scene* scene, const ptb_tile_req* req, void* rgba_dev, void* stream,
+                               ptb_render_stats* stats_out) {
+    return guarded([&] {
+        if (!req) throw ptb::Error(PTB_E_INVALID, "req is NULL");
+        ptb::render_tile_dev(scene, *req, static_cast<float4*>(rgba_dev), static_cast<cudaStream_t>(stream), stats_out);
+    });
+}
+
+ptb_status ptb_tonemap_rgba8(const float* rgb, const float* alpha, uint64_t n_pixels, uint8_t* rgba8_out) {
+    return guarded([&] { ptb::tonemap_host(rgb, alpha, n_pixels, rgba8_out); });
+}
+
+ptb_status ptb_write_png(const char* path, const uint8_t* rgba8, uint32_t w, uint32_t h) {
+    return guarded([&] {
+        if (!path || !rgba8 || !w || !h) throw ptb::Error(PTB_E_INVALID, "bad argument");
+        ptb::write_png_rgba8(path, rgba8, w, h);
+    });
+}
+
+ptb_status ptb_set_option(const char* name, int64_t value) {
+    return guarded([&] {
+        if (!name) throw ptb::Error(PTB_E_INVALID, "name is NULL");
+        const std::string n(name);
+        if (n == "wave_paths") {
+            if (value < 1024) throw ptb::Error(PTB_E_INVALID, "wave_paths must be >= 1024");
+            ptb::g_options.wave_paths = value;
+        } else if (n == "count_visits") {
+            ptb::g_options.count_visits = value ? 1 : 0;
+        } else if (n == "extend_blocks_per_sm") {
+            if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_blocks_per_sm out of range");
+            ptb::g_options.extend_blocks_per_sm = value;
+        } else if (n == "shade_blocks_per_sm") {
+            if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "shade_blocks_per_sm out of range");
+            ptb::g_options.shade_blocks_per_sm = value;
+        } else {
+            throw ptb::Error(PTB_E_INVALID, "unknown option: " + n);
+        }
+    });
+}
+
+const char* ptb_last_error(void) { return tl_error.c_str(); }
+int ptb_abi_version(void) { return PTB_ABI_VERSION; }
+int ptb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+int ptb_extend_registers(void) { return ptb::extend_regs_per_thread(); }
+
+} // extern "C"

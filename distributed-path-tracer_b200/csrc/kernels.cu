@@ -1,0 +1,582 @@
+// kernels.cu — the wavefront kernels (sm_100a) and their launch wrappers.
+//
+//   raygen      one thread per (pixel, sample) of the wave   LIB/core/renderer.cpp:359-370, APP worker.cpp:117-146
+//   extend      persistent warps pulling 32-ray batches from an atomic head;
+//               closest hit per ray (trace_device.cuh)        LIB/core/renderer.cpp:645-675
+//   shade       one thread per live path: attributes, material, emission,
+//               (sun: shadow ray traced in place), BSDF sampling, throughput,
+//               Russian roulette; survivors are compacted into the next
+//               queue with one atomicAdd per warp             LIB/core/renderer.cpp:437-643, APP worker.cpp:285-514
+//   accumulate  one thread per pixel: the reference's sequential running
+//               mean over the wave's samples                  LIB/core/renderer.cpp:373-399
+//   tonemap     ACES approximation + sRGB encode + RGBA8      LIB/core/utils.hpp:29-36, LIB/image/image.cpp:143-154
+// (LIB = path-tracer-core/path_tracer_lib/path_tracer, APP = path-tracer-core/src/processors/worker)
+//
+// Path state travels densely with the queue (64 B per live path, ping-pong):
+//   ray_o  = (origin.xyz, path id within the wave)
+//   ray_d  = (direction.xyz, packed: bounces left | shade events | flags)
+//   thr    = (throughput.rgb, -)        rad = (radiance.rgb, alpha)
+// so extend and shade read and write fully coalesced float4 streams and no
+// kernel gathers by index.  Queue sizes live in device memory, one counter per
+// iteration, so a whole wave is enqueued without host round trips.
+//
+// Built with --fmad=false: the closest-hit arithmetic must round like the
+// reference's x86-64 SSE2 code.
+
+#include "kernels.hpp"
+#include "shade_device.cuh"
+#include "trace_device.cuh"
+
+#include "ptb.h"
+
+namespace ptb {
+
+namespace {
+
+constexpr int EXT_THREADS = 128;
+constexpr int SHADE_THREADS = 128;
+constexpr size_t STACK_SMEM_BYTES = size_t(KD_STACK_DEPTH) * 3 * sizeof(uint32_t); // per thread
+
+// flags packed in ray_d.w
+constexpr uint32_t F_BOUNCE_MASK = 0xFFu;  // bounces remaining
+constexpr uint32_t F_EVENT_SHIFT = 8;      // shade events so far (RNG counter), 16 bits
+constexpr uint32_t F_EVENT_MASK = 0xFFFFu;
+constexpr uint32_t F_PRIMARY = 1u << 24;   // no opaque surface interaction yet (alpha bookkeeping of renderer::trace)
+
+__device__ __forceinline__ KdStack make_stack(uint32_t* smem) {
+    KdStack s;
+    s.base = smem + threadIdx.x;
+    s.stride = blockDim.x;
+    return s;
+}
+
+// Path p of the wave → sample s = p / padded_pixels, slot q = p % padded_pixels;
+// slots walk the tile in 8x4 pixel blocks so that a warp's primary rays form a
+// compact bundle.
+__device__ __forceinline__ bool slot_to_pixel(const WaveGeom& g, uint32_t q, uint32_t& x, uint32_t& y) {
+    const uint32_t blk = q >> 5, in = q & 31u;
+    const uint32_t bx = blk % g.blocks_x, by = blk / g.blocks_x;
+    x = bx * 8 + (in & 7u);
+    y = by * 4 + (in >> 3);
+    return x < g.w && y < g.h;
+}
+
+__device__ __forceinline__ uint32_t pixel_to_slot(const WaveGeom& g, uint32_t x, uint32_t y) {
+    return (((y >> 2) * g.blocks_x + (x >> 3)) << 5) + ((y & 3u) << 3) + (x & 7u);
+}
+
+// ------------------------------------------------------------- raygen ------
+
+__global__ void __launch_bounds__(256)
+    raygen_kernel(DScene S, WaveGeom g, RenderParams rp, PathBuffers out, float4* __restrict__ sample_out,
+                  uint32_t* __restrict__ qcount) {
+    const uint32_t n = g.padded_pixels * g.wave_samples; // multiple of 32
+    const int lane = threadIdx.x & 31;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint32_t s = p / g.padded_pixels, q = p - s * g.padded_pixels;
+        uint32_t x, y;
+        const bool valid = slot_to_pixel(g, q, x, y);
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, valid);
+        uint32_t base = 0;
+        if (lane == 0 && mask) base = atomicAdd(qcount, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (!valid) continue;
+        const uint32_t k = base + __popc(mask & ((1u << lane) - 1u));
+        const uint32_t gx = g.x0 + x, gy = g.y0 + y;
+        const uint32_t sample = g.first_sample + s;
+        float aax = 0.0f, aay = 0.0f;
+        if (!(sample == 0 && rp.first_sample_unjittered)) {
+            const Philox ph{rp.seed_lo, rp.seed_hi};
+            const uint4 r = ph(gy * g.full_w + gx, sample, 0xFFFFFFFFu, 0u);
+            aax = u01(r.x);
+            aay = u01(r.y);
+        }
+        const Ray ray = camera_ray(S.camera, gx, gy, aax, aay, g.full_w, g.full_h);
+        out.ray_o[k] = make_float4(ray.o.x, ray.o.y, ray.o.z, __uint_as_float(p));
+        out.ray_d[k] =
+            make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float((rp.max_depth & F_BOUNCE_MASK) | F_PRIMARY));
+        out.thr[k] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        // worker::trace_iter starts alpha at the background value (worker.cpp:299); renderer::trace has no such state
+        const float alpha0 = (rp.integrator == 1 && S.transparent_background) ? 0.0f : 1.0f;
+        out.rad[k] = make_float4(0.0f, 0.0f, 0.0f, alpha0);
+        // bounce_count == 0: trace returns fvec4::future, trace_iter returns (0, alpha0)
+        sample_out[p] = make_float4(0.0f, 0.0f, 0.0f, alpha0);
+    }
+}
+
+// ------------------------------------------------------------- extend ------
+
+template <bool COUNT>
+__global__ void __launch_bounds__(EXT_THREADS)
+    extend_kernel(DScene S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                  uint4* __restrict__ hits, float* __restrict__ t_out, const uint32_t* __restrict__ n_ptr,
+                  uint32_t* __restrict__ head, DeviceCounters* __restrict__ counters) {
+    extern __shared__ uint32_t smem[];
+    const KdStack stack = make_stack(smem);
+    const uint32_t n = *n_ptr;
+    const int lane = threadIdx.x & 31;
+    TraceCounters cnt{0, 0, 0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(head, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t k = base + lane;
+        if (k < n) {
+            const float4 o4 = ray_o[k], d4 = ray_d[k];
+            const SceneHit h = scene_closest<COUNT>(S, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, stack, cnt);
+            uint4 rec;
+            rec.x = (h.t >= 0) ? ((h.instance << HIT_SURFACE_BITS) | h.surface) : HIT_MISS;
+            rec.y = h.tri;
+            rec.z = __float_as_uint(h.beta);
+            rec.w = __float_as_uint(h.gamma);
+            hits[k] = rec;
+            if (t_out) t_out[k] = h.t;
+            cnt.rays++;
+        }
+    }
+    // one atomic per warp for the ray count (always), visit counters only when asked for
+    unsigned long long r = cnt.rays;
+    for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
+    if (lane == 0 && r) atomicAdd(&counters->rays, r);
+    if (COUNT) {
+        unsigned long long a = cnt.node_visits, b = cnt.leaf_visits, c = cnt.tri_tests;
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+            c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&counters->node_visits, a);
+            atomicAdd(&counters->leaf_visits, b);
+            atomicAdd(&counters->tri_tests, c);
+        }
+    }
+}
+
+// -------------------------------------------------------------- shade ------
+
+struct PathState {
+    V3 o, d;
+    V3 thr;
+    V3 rad;
+    float alpha;
+    uint32_t p;     // path id within the wave
+    uint32_t flags; // see F_*
+};
+
+// math::is_approx (LIB/math/math.inl:49-52)
+__device__ __forceinline__ bool is_approx(float a, float b) { return a == b || fabsf(a - b) < kEpsilon; }
+
+// Shades one path.  Returns true when the path continues (state updated in
+// place), false when it ended (result holds what the pixel sample receives).
+template <bool APP_RR, bool HAS_SUN>
+__device__ __forceinline__ bool shade_path(const DScene& S, const WaveGeom& g, const RenderParams& rp, PathState& st,
+                                           const uint4 hit, const KdStack& stack, TraceCounters& cnt, float4& result) {
+    const uint32_t bounce = st.flags & F_BOUNCE_MASK;
+    const uint32_t event = (st.flags >> F_EVENT_SHIFT) & F_EVENT_MASK;
+    const bool primary = (st.flags & F_PRIMARY) != 0;
+    const float bg_alpha = S.transparent_background ? 0.0f : 1.0f;
+
+    if (hit.x == HIT_MISS) { // renderer.cpp:443-451, worker.cpp:307-317 (environment texture: not supported)
+        st.rad = st.rad + st.thr * S.environment;
+        const float a = APP_RR ? bg_alpha : (primary ? bg_alpha : 1.0f);
+        result = make_float4(st.rad.x, st.rad.y, st.rad.z, a);
+        return false;
+    }
+
+    const uint32_t instance = hit.x >> HIT_SURFACE_BITS, surface = hit.x & ((1u << HIT_SURFACE_BITS) - 1u);
+    const HitAttrs at = hit_attributes(S, instance, surface, hit.y, __uint_as_float(hit.z), __uint_as_float(hit.w));
+    const MatSample m = material_sample(S, at.material, at.u, at.v);
+
+    // random numbers of this shade event: a = (opacity, lobe, u1, u2), b = (sun phi, sun theta, roulette, -)
+    const uint32_t s = st.p / g.padded_pixels, q = st.p - s * g.padded_pixels;
+    uint32_t x, y;
+    slot_to_pixel(g, q, x, y);
+    const uint32_t pixel_id = (g.y0 + y) * g.full_w + (g.x0 + x);
+    const uint32_t sample = g.first_sample + s;
+    const Philox ph{rp.seed_lo, rp.seed_hi};
+    const uint4 ra = ph(pixel_id, sample, event, 0u);
+    const uint32_t next_event = (event + 1u) & F_EVENT_MASK;
+
+    if (APP_RR) {
+        st.alpha = 1.0f;                         // worker.cpp:320
+        st.rad = st.rad + st.thr * m.emissive;   // worker.cpp:331 — before the opacity test
+    }
+
+    // stochastic opacity: continue along the same direction, same bounce (renderer.cpp:466-472, worker.cpp:334-341)
+    if (!is_approx(m.opacity, 1.0f) && u01(ra.x) > m.opacity) {
+        st.o = at.position + st.d * kEpsilon;
+        st.d = normalize(st.d); // geometry::ray's constructor normalises again
+        st.flags = bounce | (next_event << F_EVENT_SHIFT) | (st.flags & F_PRIMARY);
+        return true;
+    }
+
+    const V3 normal = shading_normal(at, m.normal_map);
+    const V3 outcoming = -st.d;
+    if (!APP_RR) st.alpha = 1.0f;
+
+    if (dot(normal, outcoming) <= 0) { // renderer.cpp:478-479 returns black; worker.cpp:348-350 keeps what it has
+        result = make_float4(st.rad.x, st.rad.y, st.rad.z, 1.0f);
+        return false;
+    }
+
+    uint4 rb = make_uint4(0, 0, 0, 0);
+    if (HAS_SUN || APP_RR) rb = ph(pixel_id, sample, event, 1u);
+
+    // sun direction for this event, shared by the shadow-catcher test and direct lighting
+    V3 direct_incoming{0.0f, 0.0f, 0.0f};
+    bool sun_visible = false, sun_above = false;
+    if (HAS_SUN) {
+        direct_incoming = rand_cone_vec(u01(rb.x), cosf(u01(rb.y) * S.sun.angular_radius), S.sun.direction);
+        sun_above = dot(normal, direct_incoming) > 0;
+        if (sun_above) {
+            const V3 so = at.position + direct_incoming * kEpsilon;
+            const SceneHit sh = scene_closest<false>(S, so, normalize(direct_incoming), stack, cnt);
+            cnt.rays++;
+            sun_visible = !(sh.t >= 0);
+        }
+    }
+
+    if (APP_RR && m.shadow_catcher && bounce == rp.max_depth) { // worker.cpp:353-389
+        if (!(HAS_SUN && sun_visible)) {
+            result = make_float4(0.0f, 0.0f, 0.0f, 1.0f); // fvec4::future
+            return false;
+        }
+        st.o = at.position + st.d * kEpsilon;
+        st.d = normalize(st.d);
+        st.flags = bounce | (next_event << F_EVENT_SHIFT) | (st.flags & F_PRIMARY);
+        return true;
+    }
+
+    const float roughness = rmax(m.roughness, 0.05F);
+    float specular_probability = fresnel_schlick(outcoming, reflect(-outcoming, normal), m.ior);
+    specular_probability = rmax(specular_probability, m.metallic);
+    const bool specular_sample = u01(ra.y) < specular_probability;
+
+    V3 direct_out{0.0f, 0.0f, 0.0f};
+    if (HAS_SUN && sun_above) {
+        if (sun_visible) {
+            if (!APP_RR && m.shadow_catcher && bounce == rp.max_depth) { // renderer.cpp:513-519
+                st.o = at.position + st.d * kEpsilon;
+                st.d = normalize(st.d);
+                st.flags = bounce | (next_event << F_EVENT_SHIFT) | F_PRIMARY;
+                return true;
+            }
+            V3 brdf;
+            float pdf;
+            eval_brdf(normal, outcoming, direct_incoming, m.albedo, roughness, m.metallic, specular_probability, brdf,
+                      pdf);
+            pdf = rlerp(1.0f, 1.0f, specular_probability); // "100% chance of hitting the sun"
+            direct_out = brdf * S.sun.energy / rmax(pdf, kEpsilon);
+            direct_out = clamp3(direct_out, V3{0.0f, 0.0f, 0.0f}, S.sun.energy);
+        } else if (!APP_RR && m.shadow_catcher && bounce == rp.max_depth) { // renderer.cpp:560-561
+            result = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+            return false;
+        }
+    }
+    if (APP_RR)
+        st.rad = st.rad + st.thr * direct_out; // worker.cpp:448
+    else
+        st.rad = st.rad + st.thr * (direct_out + m.emissive); // renderer.cpp:642, unrolled
+
+    const V3 incoming = specular_sample ? importance_ggx(u01(ra.z), u01(ra.w), normal, outcoming, roughness)
+                                        : importance_lambert(u01(ra.z), u01(ra.w), normal);
+    if (!(dot(normal, incoming) > 0)) { // renderer.cpp:578, worker.cpp:504-507
+        result = make_float4(st.rad.x, st.rad.y, st.rad.z, st.alpha);
+        return false;
+    }
+    V3 brdf;
+    float pdf;
+    eval_brdf(normal, outcoming, incoming, m.albedo, roughness, m.metallic, specular_probability, brdf, pdf);
+    const V3 k = brdf / rmax(pdf, kEpsilon);
+    if (APP_RR) {
+        st.thr = clamp3(st.thr * k, V3{0.0f, 0.0f, 0.0f}, V3{10.0f, 10.0f, 10.0f}); // worker.cpp:485-488
+    } else {
+        // clamp(k * Lin, 0, Lin) with Lin >= 0 is min(max(k,0),1) * Lin (renderer.cpp:617-620)
+        st.thr = st.thr * clamp3(k, V3{0.0f, 0.0f, 0.0f}, V3{1.0f, 1.0f, 1.0f});
+    }
+    st.o = at.position + incoming * kEpsilon;
+    st.d = normalize(incoming);
+    if (APP_RR && (int)bounce < (int)rp.max_depth - 2) { // worker.cpp:497-503
+        const float pr = rmax(st.thr.x, rmax(st.thr.y, st.thr.z));
+        if (u01(rb.z) > pr) {
+            result = make_float4(st.rad.x, st.rad.y, st.rad.z, st.alpha);
+            return false;
+        }
+        st.thr = st.thr / pr;
+    }
+    const uint32_t left = bounce - 1u;
+    if (left == 0) { // trace(0, ...) contributes nothing; trace_iter's loop ends
+        result = make_float4(st.rad.x, st.rad.y, st.rad.z, st.alpha);
+        return false;
+    }
+    st.flags = left | (next_event << F_EVENT_SHIFT);
+    return true;
+}
+
+template <bool APP_RR, bool HAS_SUN>
+__global__ void __launch_bounds__(SHADE_THREADS)
+    shade_kernel(DScene S, WaveGeom g, RenderParams rp, PathBuffers in, const uint4* __restrict__ hits,
+                 PathBuffers out, float4* __restrict__ sample_out, const uint32_t* __restrict__ n_ptr,
+                 uint32_t* __restrict__ n_next, DeviceCounters* __restrict__ counters) {
+    extern __shared__ uint32_t smem[];
+    const KdStack stack = make_stack(smem);
+    const uint32_t n = *n_ptr;
+    const int lane = threadIdx.x & 31;
+    TraceCounters cnt{0, 0, 0, 0};
+    const uint32_t n_warp = (n + 31u) & ~31u;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_warp; k += gridDim.x * blockDim.x) {
+        bool alive = false;
+        PathState st;
+        if (k < n) {
+            const float4 o4 = in.ray_o[k], d4 = in.ray_d[k], t4 = in.thr[k], r4 = in.rad[k];
+            st.o = V3{o4.x, o4.y, o4.z};
+            st.d = V3{d4.x, d4.y, d4.z};
+            st.thr = V3{t4.x, t4.y, t4.z};
+            st.rad = V3{r4.x, r4.y, r4.z};
+            st.alpha = r4.w;
+            st.p = __float_as_uint(o4.w);
+            st.flags = __float_as_uint(d4.w);
+            float4 result;
+            alive = shade_path<APP_RR, HAS_SUN>(S, g, rp, st, hits[k], stack, cnt, result);
+            if (!alive) sample_out[st.p] = result;
+        }
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, alive);
+        uint32_t base = 0;
+        if (lane == 0 && mask) base = atomicAdd(n_next, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (alive) {
+            const uint32_t k2 = base + __popc(mask & ((1u << lane) - 1u));
+            out.ray_o[k2] = make_float4(st.o.x, st.o.y, st.o.z, __uint_as_float(st.p));
+            out.ray_d[k2] = make_float4(st.d.x, st.d.y, st.d.z, __uint_as_float(st.flags));
+            out.thr[k2] = make_float4(st.thr.x, st.thr.y, st.thr.z, 0.0f);
+            out.rad[k2] = make_float4(st.rad.x, st.rad.y, st.rad.z, st.alpha);
+        }
+    }
+    if (HAS_SUN) {
+        unsigned long long r = cnt.rays;
+        for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
+        if (lane == 0 && r) atomicAdd(&counters->rays, r);
+    }
+}
+
+// ---------------------------------------------------------- accumulate -----
+
+// The reference blends sample after sample, in order (renderer.cpp:373-399):
+// `sample` is the global sample index, so waves can be chained.
+__global__ void __launch_bounds__(256)
+    accumulate_kernel(WaveGeom g, const float4* __restrict__ sample_out, float4* __restrict__ accum,
+                      uint8_t* __restrict__ claimed, bool transparent) {
+    const uint32_t npix = g.w * g.h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const uint32_t x = i % g.w, y = i / g.w;
+        const uint32_t q = pixel_to_slot(g, x, y);
+        float4 px = accum[i];
+        bool cl = transparent ? (claimed[i] != 0) : false;
+        for (uint32_t s = 0; s < g.wave_samples; s++) {
+            const float4 d = sample_out[size_t(s) * g.padded_pixels + q];
+            const uint32_t sample = g.first_sample + s;
+            if (transparent) {
+                if (d.w > 0.5 && !cl) {
+                    px.x = d.x; px.y = d.y; px.z = d.z;
+                    px.w = float(1u / (sample + 1u)); // integer division, as written in the reference
+                    cl = true;
+                    continue;
+                } else if (d.w < 0.5 && cl) {
+                    px.w = px.w * float(sample) + d.w;
+                    px.w = px.w / float(sample + 1u);
+                    continue;
+                } else if (d.w < 0.5) {
+                    continue;
+                }
+            }
+            const float fs = float(sample), fs1 = float(sample + 1u);
+            px.x = (px.x * fs + d.x) / fs1;
+            px.y = (px.y * fs + d.y) / fs1;
+            px.z = (px.z * fs + d.z) / fs1;
+            px.w = (px.w * fs + d.w) / fs1;
+        }
+        accum[i] = px;
+        if (transparent) claimed[i] = cl ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------- tonemap -----
+
+__device__ __forceinline__ float aces(float hdr) { // tonemap_approx_aces, per component
+    const float a = 2.51F, b = 0.03F, c = 2.43F, d = 0.59F, e = 0.14F;
+    const float v = (hdr * (a * hdr + b)) / (hdr * (c * hdr + d) + e);
+    return rclamp(v, 0.0f, 1.0f);
+}
+
+__global__ void tonemap_kernel(const float* __restrict__ rgb, const float* __restrict__ alpha, uint64_t n,
+                               uint8_t* __restrict__ rgba8) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uchar4 o;
+        // image::write: sRGB encode pow(v, 1/2.2F), then uint8(v * 255 + 0.5F)
+        o.x = (unsigned char)(powf(aces(rgb[3 * i]), 1 / 2.2F) * 255 + 0.5F);
+        o.y = (unsigned char)(powf(aces(rgb[3 * i + 1]), 1 / 2.2F) * 255 + 0.5F);
+        o.z = (unsigned char)(powf(aces(rgb[3 * i + 2]), 1 / 2.2F) * 255 + 0.5F);
+        o.w = (unsigned char)((alpha ? alpha[i] : 1.0f) * 255 + 0.5F);
+        reinterpret_cast<uchar4*>(rgba8)[i] = o;
+    }
+}
+
+__global__ void split_rgba_kernel(const float4* __restrict__ rgba, uint64_t n, float* __restrict__ rgb,
+                                  float* __restrict__ alpha) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 v = rgba[i];
+        rgb[3 * i] = v.x;
+        rgb[3 * i + 1] = v.y;
+        rgb[3 * i + 2] = v.z;
+        if (alpha) alpha[i] = v.w;
+    }
+}
+
+// ------------------------------------------------- explicit ray sets -------
+
+__global__ void prep_rays_kernel(const float* __restrict__ od, uint64_t n, float4* __restrict__ ray_o,
+                                 float4* __restrict__ ray_d) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const V3 d = normalize(V3{od[6 * i + 3], od[6 * i + 4], od[6 * i + 5]}); // geometry::ray::ray, ray.cpp:6-8
+        ray_o[i] = make_float4(od[6 * i], od[6 * i + 1], od[6 * i + 2], 0.0f);
+        ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    }
+}
+
+__global__ void export_hits_kernel(DScene S, const uint4* __restrict__ hits, const float* __restrict__ t, uint64_t n,
+                                   ptb_hit* __restrict__ out, float* __restrict__ attrs) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 h = hits[i];
+        ptb_hit o;
+        if (h.x == HIT_MISS) {
+            o.instance = o.surface = o.triangle = PTB_MISS;
+            o.t = -1.0f;
+            o.bary[0] = o.bary[1] = o.bary[2] = 0.0f;
+        } else {
+            const float beta = __uint_as_float(h.z), gamma = __uint_as_float(h.w);
+            o.instance = h.x >> HIT_SURFACE_BITS;
+            o.surface = h.x & ((1u << HIT_SURFACE_BITS) - 1u);
+            o.triangle = h.y;
+            o.t = t[i];
+            o.bary[0] = 1 - beta - gamma;
+            o.bary[1] = beta;
+            o.bary[2] = gamma;
+        }
+        out[i] = o;
+        if (attrs) {
+            float* a = attrs + 14 * i;
+            if (h.x == HIT_MISS) {
+                for (int j = 0; j < 14; j++) a[j] = 0.0f;
+            } else {
+                const HitAttrs at = hit_attributes(S, o.instance, o.surface, o.triangle, o.bary[1], o.bary[2]);
+                const MatSample m = material_sample(S, at.material, at.u, at.v);
+                const V3 sn = shading_normal(at, m.normal_map);
+                a[0] = at.position.x; a[1] = at.position.y; a[2] = at.position.z;
+                a[3] = at.u; a[4] = at.v;
+                a[5] = at.normal.x; a[6] = at.normal.y; a[7] = at.normal.z;
+                a[8] = at.tangent.x; a[9] = at.tangent.y; a[10] = at.tangent.z;
+                a[11] = sn.x; a[12] = sn.y; a[13] = sn.z;
+            }
+        }
+    }
+}
+
+__global__ void camera_rays_kernel(DScene S, uint32_t w, uint32_t h, const uint32_t* __restrict__ px,
+                                   const uint32_t* __restrict__ py, const float* __restrict__ aa, uint64_t n,
+                                   float* __restrict__ od) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const Ray r = camera_ray(S.camera, px[i], py[i], aa[2 * i], aa[2 * i + 1], w, h);
+        od[6 * i] = r.o.x; od[6 * i + 1] = r.o.y; od[6 * i + 2] = r.o.z;
+        od[6 * i + 3] = r.d.x; od[6 * i + 4] = r.d.y; od[6 * i + 5] = r.d.z;
+    }
+}
+
+inline int grid_for(uint64_t n, int threads, int cap) {
+    uint64_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > (uint64_t)cap) b = cap;
+    return (int)b;
+}
+
+} // namespace
+
+// ------------------------------------------------------------ launchers ----
+
+void launch_raygen(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& out,
+                   float4* sample_out, uint32_t* qcount0, const LaunchCfg& cfg, cudaStream_t st) {
+    const uint64_t n = uint64_t(g.padded_pixels) * g.wave_samples;
+    raygen_kernel<<<grid_for(n, 256, cfg.sm_count * 8), 256, 0, st>>>(S, g, rp, out, sample_out, qcount0);
+}
+
+void launch_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
+                   const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
+                   cudaStream_t st) {
+    const size_t smem = STACK_SMEM_BYTES * EXT_THREADS;
+    const int grid = cfg.sm_count * cfg.extend_blocks_per_sm;
+    if (cfg.count_visits)
+        extend_kernel<true><<<grid, EXT_THREADS, smem, st>>>(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters);
+    else
+        extend_kernel<false><<<grid, EXT_THREADS, smem, st>>>(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters);
+}
+
+void launch_shade(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& in,
+                  const uint4* hits, const PathBuffers& out, float4* sample_out, const uint32_t* n_ptr,
+                  uint32_t* n_next, DeviceCounters* counters, const LaunchCfg& cfg, cudaStream_t st) {
+    const int grid = cfg.sm_count * cfg.shade_blocks_per_sm;
+    const bool sun = S.sun.enabled != 0;
+    const size_t smem = sun ? STACK_SMEM_BYTES * SHADE_THREADS : 0;
+    if (rp.integrator == 1) {
+        if (sun)
+            shade_kernel<true, true><<<grid, SHADE_THREADS, smem, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr,
+                                                                         n_next, counters);
+        else
+            shade_kernel<true, false><<<grid, SHADE_THREADS, smem, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr,
+                                                                          n_next, counters);
+    } else {
+        if (sun)
+            shade_kernel<false, true><<<grid, SHADE_THREADS, smem, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr,
+                                                                          n_next, counters);
+        else
+            shade_kernel<false, false><<<grid, SHADE_THREADS, smem, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr,
+                                                                           n_next, counters);
+    }
+}
+
+void launch_accumulate(const WaveGeom& g, const float4* sample_out, float4* accum, uint8_t* claimed, bool transparent,
+                       cudaStream_t st) {
+    const uint64_t n = uint64_t(g.w) * g.h;
+    accumulate_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(g, sample_out, accum, claimed, transparent);
+}
+
+void launch_tonemap(const float* rgb, const float* alpha, uint64_t n, uint8_t* rgba8, cudaStream_t st) {
+    tonemap_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(rgb, alpha, n, rgba8);
+}
+
+void launch_split_rgba(const float4* rgba, uint64_t n, float* rgb, float* alpha, cudaStream_t st) {
+    split_rgba_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(rgba, n, rgb, alpha);
+}
+
+void launch_prep_rays(const float* origin_dir, uint64_t n, float4* ray_o, float4* ray_d, cudaStream_t st) {
+    prep_rays_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(origin_dir, n, ray_o, ray_d);
+}
+
+void launch_export_hits(const DScene& S, const uint4* hits, const float* t, uint64_t n, void* hits_out, float* attrs_out,
+                        cudaStream_t st) {
+    export_hits_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(S, hits, t, n, static_cast<ptb_hit*>(hits_out),
+                                                                   attrs_out);
+}
+
+void launch_camera_rays(const DScene& S, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py, const float* aa,
+                        uint64_t n, float* origin_dir, cudaStream_t st) {
+    camera_rays_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(S, w, h, px, py, aa, n, origin_dir);
+}
+
+int extend_regs_per_thread() {
+    cudaFuncAttributes a{};
+    if (cudaFuncGetAttributes(&a, extend_kernel<false>) != cudaSuccess) return -1;
+    return a.numRegs;
+}
+
+} // namespace ptb

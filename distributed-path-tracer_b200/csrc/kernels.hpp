@@ -1,0 +1,75 @@
+// kernels.hpp — launch interface between the wavefront driver (render.cu) and kernels.cu.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_scene.hpp"
+
+namespace ptb {
+
+// Hit record written by extend and read by shade: 16 bytes.
+//   x = instance << 12 | surface ordinal   (0xFFFFFFFF: miss)
+//   y = triangle index inside the mesh
+//   z = beta bits, w = gamma bits          (alpha = 1 - beta - gamma)
+constexpr uint32_t HIT_MISS = 0xFFFFFFFFu;
+constexpr uint32_t HIT_SURFACE_BITS = 12;
+
+struct WaveGeom {
+    uint32_t full_w, full_h;       // frame resolution (camera aspect, ndc)
+    uint32_t x0, y0, w, h;         // tile
+    uint32_t blocks_x, blocks_y;   // tile in 8x4-pixel blocks
+    uint32_t padded_pixels;        // blocks_x * blocks_y * 32
+    uint32_t wave_samples;         // samples of every pixel in this wave
+    uint32_t first_sample;         // global index of the wave's first sample
+};
+
+struct RenderParams {
+    uint32_t seed_lo, seed_hi;
+    uint32_t max_depth;
+    uint32_t integrator; // 0: LIB (renderer::trace), 1: APP_RR (worker::trace_iter)
+    uint32_t first_sample_unjittered;
+};
+
+struct PathBuffers { // one of the two ping-pong sets, each array `capacity` float4
+    float4* ray_o;
+    float4* ray_d;
+    float4* thr;
+    float4* rad;
+};
+
+struct DeviceCounters {
+    unsigned long long node_visits, leaf_visits, tri_tests, rays;
+};
+
+struct LaunchCfg {
+    int sm_count;
+    int extend_blocks_per_sm;
+    int shade_blocks_per_sm;
+    bool count_visits;
+};
+
+// qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.
+void launch_raygen(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& out,
+                   float4* sample_out, uint32_t* qcount0, const LaunchCfg& cfg, cudaStream_t st);
+void launch_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
+                   const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
+                   cudaStream_t st);
+void launch_shade(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& in,
+                  const uint4* hits, const PathBuffers& out, float4* sample_out, const uint32_t* n_ptr,
+                  uint32_t* n_next, DeviceCounters* counters, const LaunchCfg& cfg, cudaStream_t st);
+void launch_accumulate(const WaveGeom& g, const float4* sample_out, float4* accum, uint8_t* claimed,
+                       bool transparent, cudaStream_t st);
+void launch_tonemap(const float* rgb, const float* alpha, uint64_t n, uint8_t* rgba8, cudaStream_t st);
+void launch_split_rgba(const float4* rgba, uint64_t n, float* rgb, float* alpha, cudaStream_t st);
+
+// explicit ray sets (ptb_trace_rays): normalise directions like geometry::ray's constructor, then export
+void launch_prep_rays(const float* origin_dir, uint64_t n, float4* ray_o, float4* ray_d, cudaStream_t st);
+void launch_export_hits(const DScene& S, const uint4* hits, const float* t, uint64_t n, void* hits_out /*ptb_hit*/,
+                        float* attrs_out /*14 per ray or null*/, cudaStream_t st);
+void launch_camera_rays(const DScene& S, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py,
+                        const float* aa, uint64_t n, float* origin_dir, cudaStream_t st);
+
+int extend_regs_per_thread();
+
+} // namespace ptb

@@ -1,0 +1,320 @@
+// render.cu — the wavefront driver: what renderer::render's sample/row loops
+// (LIB/core/renderer.cpp:354-407) and the worker's queue pipeline
+// (APP/processors/worker/worker.cpp:46-68) become on one GPU.
+//
+// One wave = wave_samples consecutive samples of every pixel of the tile.  For
+// each wave: raygen, then at most max_depth iterations of
+//     extend (closest hit for every live path) → shade (terminate or emit the next ray)
+// with the queue size of iteration i held in device memory (qcount[i]), so the
+// host enqueues a whole wave without waiting; accumulate then folds the wave's
+// samples into the running mean in sample order.  Extra iterations (stochastic
+// opacity, shadow-catcher pass-through do not consume a bounce) are driven by
+// one host read-back per extra iteration and only happen for such scenes.
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "errors.hpp"
+#include "kernels.hpp"
+#include "render.hpp"
+#include "scene.hpp"
+
+namespace ptb {
+
+Options g_options;
+
+namespace {
+
+constexpr uint32_t MAX_EXTRA_ITERS = 256; // pass-through events per path beyond max_depth before giving up
+
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t need) {
+        if (need <= bytes) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        PTB_CUDA(cudaMalloc(&p, need));
+        bytes = need;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+// Per-device scratch, reused across calls (allocation is not part of the hot path).
+struct Workspace {
+    DeviceBuf path[2][4]; // ping-pong × {ray_o, ray_d, thr, rad}
+    DeviceBuf hits, t, sample_out, counters, qcount, accum, claimed, io_a, io_b, io_c;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::mutex lock;
+    void events() {
+        for (auto& e : ev)
+            if (!e) PTB_CUDA(cudaEventCreate(&e));
+    }
+};
+
+Workspace& workspace(int device) {
+    static std::mutex m;
+    static std::vector<Workspace*> ws;
+    std::lock_guard<std::mutex> g(m);
+    if ((int)ws.size() <= device) ws.resize(device + 1, nullptr);
+    if (!ws[device]) ws[device] = new Workspace;
+    return *ws[device];
+}
+
+PathBuffers path_set(Workspace& w, int i) {
+    return PathBuffers{(float4*)w.path[i][0].p, (float4*)w.path[i][1].p, (float4*)w.path[i][2].p,
+                       (float4*)w.path[i][3].p};
+}
+
+LaunchCfg launch_cfg(const ptb_scene* s) {
+    LaunchCfg c;
+    c.sm_count = s->sm_count;
+    c.extend_blocks_per_sm = (int)g_options.extend_blocks_per_sm;
+    c.shade_blocks_per_sm = (int)g_options.shade_blocks_per_sm;
+    c.count_visits = g_options.count_visits != 0;
+    return c;
+}
+
+} // namespace
+
+void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_dev, cudaStream_t st,
+                     ptb_render_stats* stats) {
+    if (!s || !rgba_dev) throw Error(PTB_E_INVALID, "scene or output is NULL");
+    if (req.w == 0 || req.h == 0 || req.full_w == 0 || req.full_h == 0) throw Error(PTB_E_INVALID, "empty tile or frame");
+    if (uint64_t(req.x0) + req.w > req.full_w || uint64_t(req.y0) + req.h > req.full_h)
+        throw Error(PTB_E_INVALID, "tile exceeds the frame");
+    if (req.max_depth > 255) throw Error(PTB_E_INVALID, "max_depth above 255 (the reference's bounce_count is uint8_t)");
+    if (req.integrator > 1) throw Error(PTB_E_INVALID, "unknown integrator");
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device);
+    std::lock_guard<std::mutex> guard(w.lock);
+    w.events();
+
+    WaveGeom g{};
+    g.full_w = req.full_w; g.full_h = req.full_h;
+    g.x0 = req.x0; g.y0 = req.y0; g.w = req.w; g.h = req.h;
+    g.blocks_x = (req.w + 7) / 8;
+    g.blocks_y = (req.h + 3) / 4;
+    const uint64_t padded = uint64_t(g.blocks_x) * g.blocks_y * 32;
+    if (padded >= (1ull << 31)) throw Error(PTB_E_INVALID, "tile too large");
+    g.padded_pixels = (uint32_t)padded;
+    uint64_t wave_samples = std::max<uint64_t>(1, (uint64_t)g_options.wave_paths / padded);
+    wave_samples = std::min<uint64_t>(wave_samples, std::max<uint32_t>(req.spp, 1));
+    while (wave_samples > 1 && wave_samples * padded >= (1ull << 32)) wave_samples--;
+    const uint64_t cap = wave_samples * padded;
+
+    RenderParams rp{};
+    rp.seed_lo = (uint32_t)req.seed;
+    rp.seed_hi = (uint32_t)(req.seed >> 32);
+    rp.max_depth = req.max_depth;
+    rp.integrator = req.integrator;
+    rp.first_sample_unjittered = req.first_sample_unjittered;
+
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 4; j++) w.path[i][j].ensure(cap * sizeof(float4));
+    w.hits.ensure(cap * sizeof(uint4));
+    w.sample_out.ensure(cap * sizeof(float4));
+    const uint32_t n_iters_fixed = req.max_depth;
+    const size_t n_counters = size_t(n_iters_fixed) + MAX_EXTRA_ITERS + 2;
+    w.qcount.ensure(n_counters * 2 * sizeof(uint32_t));
+    w.counters.ensure(sizeof(DeviceCounters));
+    const bool transparent = s->d.transparent_background != 0;
+    if (transparent) w.claimed.ensure(size_t(req.w) * req.h);
+
+    uint32_t* qcount = (uint32_t*)w.qcount.p;
+    uint32_t* qhead = qcount + n_counters;
+    DeviceCounters* counters = (DeviceCounters*)w.counters.p;
+    const LaunchCfg cfg = launch_cfg(s);
+
+    // May a path need more shade events than max_depth?  Only through stochastic
+    // opacity or shadow-catcher pass-through.
+    const bool may_pass_through = s->has_pass_through;
+
+    PTB_CUDA(cudaMemsetAsync(counters, 0, sizeof(DeviceCounters), st));
+    if (req.first_sample == 0) {
+        PTB_CUDA(cudaMemsetAsync(rgba_dev, 0, size_t(req.w) * req.h * sizeof(float4), st));
+        if (transparent) PTB_CUDA(cudaMemsetAsync(w.claimed.p, 0, size_t(req.w) * req.h, st));
+    }
+    PTB_CUDA(cudaEventRecord(w.ev[0], st));
+
+    uint64_t launches = 0, extend_launches = 0, paths = 0;
+    for (uint32_t s0 = 0; s0 < req.spp; s0 += (uint32_t)wave_samples) {
+        g.wave_samples = (uint32_t)std::min<uint64_t>(wave_samples, req.spp - s0);
+        g.first_sample = req.first_sample + s0;
+        paths += uint64_t(req.w) * req.h * g.wave_samples;
+        PTB_CUDA(cudaMemsetAsync(qcount, 0, n_counters * 2 * sizeof(uint32_t), st));
+        launch_raygen(s->d, g, rp, path_set(w, 0), (float4*)w.sample_out.p, &qcount[0], cfg, st);
+        launches++;
+        int cur = 0;
+        uint32_t it = 0;
+        for (; it < n_iters_fixed; it++) {
+            const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
+            launch_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg, st);
+            launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
+                         &qcount[it + 1], counters, cfg, st);
+            launches += 2;
+            extend_launches++;
+            cur ^= 1;
+        }
+        if (may_pass_through && n_iters_fixed > 0) {
+            for (uint32_t extra = 0; extra < MAX_EXTRA_ITERS; extra++, it++) {
+                uint32_t live = 0;
+                PTB_CUDA(cudaMemcpyAsync(&live, &qcount[it], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                PTB_CUDA(cudaStreamSynchronize(st));
+                if (live == 0) break;
+                const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
+                launch_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg,
+                              st);
+                launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
+                             &qcount[it + 1], counters, cfg, st);
+                launches += 2;
+                extend_launches++;
+                cur ^= 1;
+            }
+        }
+        launch_accumulate(g, (const float4*)w.sample_out.p, rgba_dev, (uint8_t*)w.claimed.p, transparent, st);
+        launches++;
+    }
+    PTB_CUDA(cudaEventRecord(w.ev[1], st));
+    PTB_CUDA(cudaGetLastError());
+
+    if (stats) {
+        DeviceCounters hc{};
+        PTB_CUDA(cudaMemcpyAsync(&hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        PTB_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        PTB_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1]));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->paths = paths;
+        stats->rays = hc.rays;
+        stats->kernel_launches = launches;
+        stats->extend_launches = extend_launches;
+        stats->gpu_seconds = ms * 1e-3;
+        stats->node_visits = hc.node_visits;
+        stats->leaf_visits = hc.leaf_visits;
+        stats->tri_tests = hc.tri_tests;
+    }
+}
+
+void render_tile_host(const ptb_scene* s, const ptb_tile_req& req, float* rgb_out, float* alpha_out,
+                      ptb_render_stats* stats) {
+    if (!s || !rgb_out) throw Error(PTB_E_INVALID, "scene or output is NULL");
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device);
+    const size_t npix = size_t(req.w) * req.h;
+    {
+        std::lock_guard<std::mutex> guard(w.lock);
+        w.accum.ensure(std::max<size_t>(npix, 1) * sizeof(float4));
+        w.io_a.ensure(std::max<size_t>(npix, 1) * 3 * sizeof(float));
+        w.io_b.ensure(std::max<size_t>(npix, 1) * sizeof(float));
+    }
+    cudaStream_t st = nullptr;
+    render_tile_dev(s, req, (float4*)w.accum.p, st, stats);
+    std::lock_guard<std::mutex> guard(w.lock);
+    launch_split_rgba((const float4*)w.accum.p, npix, (float*)w.io_a.p, alpha_out ? (float*)w.io_b.p : nullptr, st);
+    PTB_CUDA(cudaMemcpyAsync(rgb_out, w.io_a.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (alpha_out) PTB_CUDA(cudaMemcpyAsync(alpha_out, w.io_b.p, npix * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PTB_CUDA(cudaStreamSynchronize(st));
+}
+
+void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, ptb_hit* hits_out, float* attrs_out,
+                     ptb_render_stats* stats) {
+    if (!s) throw Error(PTB_E_INVALID, "scene is NULL");
+    if (n == 0) return;
+    if (!origin_dir || !hits_out) throw Error(PTB_E_INVALID, "rays or hits_out is NULL");
+    if (n >= (1ull << 31)) throw Error(PTB_E_INVALID, "too many rays in one call (max 2^31 - 1)");
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device);
+    std::lock_guard<std::mutex> guard(w.lock);
+    w.events();
+    cudaStream_t st = nullptr;
+    w.io_a.ensure(n * 6 * sizeof(float));
+    w.io_b.ensure(n * sizeof(ptb_hit));
+    if (attrs_out) w.io_c.ensure(n * 14 * sizeof(float));
+    w.path[0][0].ensure(n * sizeof(float4));
+    w.path[0][1].ensure(n * sizeof(float4));
+    w.hits.ensure(n * sizeof(uint4));
+    w.t.ensure(n * sizeof(float));
+    w.qcount.ensure(4 * sizeof(uint32_t));
+    w.counters.ensure(sizeof(DeviceCounters));
+    uint32_t* qc = (uint32_t*)w.qcount.p;
+    const uint32_t init[2] = {(uint32_t)n, 0u};
+    PTB_CUDA(cudaMemcpyAsync(qc, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
+    PTB_CUDA(cudaMemcpyAsync(w.io_a.p, origin_dir, n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    launch_prep_rays((const float*)w.io_a.p, n, (float4*)w.path[0][0].p, (float4*)w.path[0][1].p, st);
+    PTB_CUDA(cudaEventRecord(w.ev[0], st));
+    launch_extend(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint4*)w.hits.p, (float*)w.t.p,
+                  &qc[0], &qc[1], (DeviceCounters*)w.counters.p, launch_cfg(s), st);
+    PTB_CUDA(cudaEventRecord(w.ev[1], st));
+    launch_export_hits(s->d, (const uint4*)w.hits.p, (const float*)w.t.p, n, w.io_b.p,
+                       attrs_out ? (float*)w.io_c.p : nullptr, st);
+    PTB_CUDA(cudaMemcpyAsync(hits_out, w.io_b.p, n * sizeof(ptb_hit), cudaMemcpyDeviceToHost, st));
+    if (attrs_out) PTB_CUDA(cudaMemcpyAsync(attrs_out, w.io_c.p, n * 14 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DeviceCounters hc{};
+    PTB_CUDA(cudaMemcpyAsync(&hc, w.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    PTB_CUDA(cudaStreamSynchronize(st));
+    PTB_CUDA(cudaGetLastError());
+    if (stats) {
+        float ms = 0;
+        PTB_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1]));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->rays = hc.rays;
+        stats->kernel_launches = 3;
+        stats->extend_launches = 1;
+        stats->gpu_seconds = stats->extend_seconds = ms * 1e-3;
+        stats->node_visits = hc.node_visits;
+        stats->leaf_visits = hc.leaf_visits;
+        stats->tri_tests = hc.tri_tests;
+    }
+}
+
+void camera_rays_host(const ptb_scene* s, uint32_t wd, uint32_t ht, const uint32_t* px, const uint32_t* py,
+                      const float* aa, uint64_t n, float* origin_dir) {
+    if (!s) throw Error(PTB_E_INVALID, "scene is NULL");
+    if (n == 0) return;
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device);
+    std::lock_guard<std::mutex> guard(w.lock);
+    cudaStream_t st = nullptr;
+    w.io_a.ensure(n * 6 * sizeof(float));
+    w.io_b.ensure(n * 2 * sizeof(uint32_t));
+    w.io_c.ensure(n * 2 * sizeof(float));
+    uint32_t* dpx = (uint32_t*)w.io_b.p;
+    uint32_t* dpy = dpx + n;
+    PTB_CUDA(cudaMemcpyAsync(dpx, px, n * 4, cudaMemcpyHostToDevice, st));
+    PTB_CUDA(cudaMemcpyAsync(dpy, py, n * 4, cudaMemcpyHostToDevice, st));
+    PTB_CUDA(cudaMemcpyAsync(w.io_c.p, aa, n * 8, cudaMemcpyHostToDevice, st));
+    launch_camera_rays(s->d, wd, ht, dpx, dpy, (const float*)w.io_c.p, n, (float*)w.io_a.p, st);
+    PTB_CUDA(cudaMemcpyAsync(origin_dir, w.io_a.p, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PTB_CUDA(cudaStreamSynchronize(st));
+    PTB_CUDA(cudaGetLastError());
+}
+
+void tonemap_host(const float* rgb, const float* alpha, uint64_t n, uint8_t* rgba8) {
+    if (n == 0) return;
+    if (!rgb || !rgba8) throw Error(PTB_E_INVALID, "rgb or rgba8_out is NULL");
+    int dev = 0;
+    PTB_CUDA(cudaGetDevice(&dev));
+    Workspace& w = workspace(dev);
+    std::lock_guard<std::mutex> guard(w.lock);
+    cudaStream_t st = nullptr;
+    w.io_a.ensure(n * 3 * sizeof(float));
+    w.io_b.ensure(n * sizeof(float));
+    w.io_c.ensure(n * 4);
+    PTB_CUDA(cudaMemcpyAsync(w.io_a.p, rgb, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (alpha) PTB_CUDA(cudaMemcpyAsync(w.io_b.p, alpha, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    launch_tonemap((const float*)w.io_a.p, alpha ? (const float*)w.io_b.p : nullptr, n, (uint8_t*)w.io_c.p, st);
+    PTB_CUDA(cudaMemcpyAsync(rgba8, w.io_c.p, n * 4, cudaMemcpyDeviceToHost, st));
+    PTB_CUDA(cudaStreamSynchronize(st));
+    PTB_CUDA(cudaGetLastError());
+}
+
+} // namespace ptb

@@ -1,0 +1,31 @@
+// render.hpp — entry points of render.cu used by the C ABI layer (api.cu).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ptb.h"
+
+struct ptb_scene;
+
+namespace ptb {
+
+struct Options {
+    int64_t wave_paths = 8ll << 20;     // paths per wavefront (rounded to whole samples of the tile)
+    int64_t count_visits = 0;           // instrumented extend kernel (node / leaf / triangle counters)
+    int64_t extend_blocks_per_sm = 8;   // persistent extend grid = SMs x this
+    int64_t shade_blocks_per_sm = 8;
+};
+extern Options g_options;
+
+void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_dev, cudaStream_t st,
+                     ptb_render_stats* stats);
+void render_tile_host(const ptb_scene* s, const ptb_tile_req& req, float* rgb_out, float* alpha_out,
+                      ptb_render_stats* stats);
+void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, ptb_hit* hits_out, float* attrs_out,
+                     ptb_render_stats* stats);
+void camera_rays_host(const ptb_scene* s, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py,
+                      const float* aa, uint64_t n, float* origin_dir);
+void tonemap_host(const float* rgb, const float* alpha, uint64_t n, uint8_t* rgba8);
+
+} // namespace ptb

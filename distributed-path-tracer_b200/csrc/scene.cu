@@ -1,0 +1,329 @@
+// scene.cu — scene construction: validates a ptb_scene_desc, rebuilds every
+// mesh's KD-tree on the host (kd_build.cpp), flattens everything into the HBM
+// layout of device_scene.hpp and uploads it.
+//
+// Replaces, for the hot path, what renderer::get_mesh / mesh::recalculate_aabb /
+// mesh::build_kd_tree / model::recalculate_aabb set up as a shared_ptr object
+// graph (LIB/core/renderer.cpp:177-263, LIB/core/mesh.cpp:254-298,
+// LIB/scene/model.cpp:13-18; LIB = path-tracer-core/path_tracer_lib/path_tracer).
+// Host float code here is compiled without FMA contraction.
+
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+#include "errors.hpp"
+#include "kernels.hpp"
+#include "scene.hpp"
+
+namespace ptb {
+
+namespace {
+
+template <typename T>
+T* upload(ptb_scene* s, const std::vector<T>& v) {
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 256);
+    void* p = nullptr;
+    PTB_CUDA(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    s->info.device_bytes += bytes;
+    if (!v.empty()) PTB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return static_cast<T*>(p);
+}
+
+Xform xform_from(const float* origin, const float* basis) {
+    Xform t;
+    t.origin = V3{origin[0], origin[1], origin[2]};
+    t.basis = M3{V3{basis[0], basis[1], basis[2]}, V3{basis[3], basis[4], basis[5]}, V3{basis[6], basis[7], basis[8]}};
+    return t;
+}
+
+void require(bool ok, const char* msg) {
+    if (!ok) throw Error(PTB_E_INVALID, msg);
+}
+
+bool finite3(const float* p, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (!std::isfinite(p[i])) return false;
+    return true;
+}
+
+} // namespace
+
+ptb_scene_desc OwnedScene::view() {
+    mesh_views.resize(meshes.size());
+    for (size_t i = 0; i < meshes.size(); i++) {
+        mesh_views[i].positions = meshes[i].positions.data();
+        mesh_views[i].normals = meshes[i].normals.data();
+        mesh_views[i].tangents = meshes[i].tangents.data();
+        mesh_views[i].uvs = meshes[i].uvs.data();
+        mesh_views[i].n_vertices = static_cast<uint32_t>(meshes[i].positions.size() / 3);
+        mesh_views[i].indices = meshes[i].indices.data();
+        mesh_views[i].n_triangles = static_cast<uint32_t>(meshes[i].indices.size() / 3);
+    }
+    texture_views.resize(textures.size());
+    for (size_t i = 0; i < textures.size(); i++) {
+        texture_views[i].pixels = textures[i].pixels.data();
+        texture_views[i].width = textures[i].width;
+        texture_views[i].height = textures[i].height;
+        texture_views[i].channels = textures[i].channels;
+        texture_views[i].is_float = textures[i].is_float;
+        texture_views[i].srgb = textures[i].srgb;
+    }
+    ptb_scene_desc d{};
+    d.meshes = mesh_views.data();
+    d.n_meshes = static_cast<uint32_t>(meshes.size());
+    d.surfaces = surfaces.data();
+    d.n_surfaces = static_cast<uint32_t>(surfaces.size());
+    d.instances = instances.data();
+    d.n_instances = static_cast<uint32_t>(instances.size());
+    d.materials = materials.data();
+    d.n_materials = static_cast<uint32_t>(materials.size());
+    d.textures = texture_views.data();
+    d.n_textures = static_cast<uint32_t>(textures.size());
+    d.camera = camera;
+    d.sun = sun;
+    for (int i = 0; i < 3; i++) d.environment_factor[i] = environment_factor[i];
+    d.transparent_background = transparent_background;
+    d.kd_use_sah = 1;
+    d.kd_max_depth = 25;
+    return d;
+}
+
+void destroy_scene(ptb_scene* s) {
+    if (!s) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    for (void* p : s->allocs) cudaFree(p);
+    cudaSetDevice(prev);
+    delete s;
+}
+
+ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
+    // ---- validation (nothing below may read out of bounds) ----
+    require(desc.n_meshes == 0 || desc.meshes, "meshes is NULL");
+    require(desc.n_surfaces == 0 || desc.surfaces, "surfaces is NULL");
+    require(desc.n_instances == 0 || desc.instances, "instances is NULL");
+    require(desc.n_materials == 0 || desc.materials, "materials is NULL");
+    require(desc.n_textures == 0 || desc.textures, "textures is NULL");
+    require(desc.n_instances < (1u << (32 - HIT_SURFACE_BITS)), "too many instances (max 2^20 - 1)");
+    const uint32_t max_depth = desc.kd_max_depth ? desc.kd_max_depth : 25;
+    require(max_depth <= 25, "kd_max_depth above 25 is not supported (traversal stack depth)");
+    for (uint32_t m = 0; m < desc.n_meshes; m++) {
+        const ptb_mesh_desc& md = desc.meshes[m];
+        require(md.n_vertices == 0 || (md.positions && md.normals && md.tangents && md.uvs),
+                "mesh attribute pointer is NULL");
+        require(md.n_triangles == 0 || md.indices, "mesh indices is NULL");
+        for (size_t i = 0; i < size_t(md.n_triangles) * 3; i++)
+            require(md.indices[i] < md.n_vertices, "triangle index out of range");
+        require(finite3(md.positions, size_t(md.n_vertices) * 3), "non-finite vertex position");
+    }
+    for (uint32_t s = 0; s < desc.n_surfaces; s++) {
+        require(desc.surfaces[s].mesh < desc.n_meshes, "surface.mesh out of range");
+        require(desc.surfaces[s].material < desc.n_materials, "surface.material out of range");
+    }
+    for (uint32_t i = 0; i < desc.n_instances; i++) {
+        const ptb_instance_desc& id = desc.instances[i];
+        require(uint64_t(id.first_surface) + id.n_surfaces <= desc.n_surfaces, "instance surface range out of bounds");
+        require(id.n_surfaces < (1u << HIT_SURFACE_BITS), "too many surfaces in one instance (max 4095)");
+    }
+    for (uint32_t m = 0; m < desc.n_materials; m++) {
+        const ptb_material_desc& md = desc.materials[m];
+        const uint32_t slots[6] = {md.normal_tex, md.albedo_tex,   md.opacity_tex,
+                                   md.roughness_tex, md.metallic_tex, md.emissive_tex};
+        for (uint32_t t : slots) require(t == PTB_NO_TEXTURE || t < desc.n_textures, "material texture id out of range");
+    }
+    for (uint32_t t = 0; t < desc.n_textures; t++) {
+        const ptb_texture_desc& td = desc.textures[t];
+        require(td.pixels && td.width && td.height && td.channels >= 1 && td.channels <= 4, "bad texture");
+    }
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        throw Error(PTB_E_CUDA, "no CUDA device is usable; libptb has no CPU fallback");
+    require(device >= 0 && device < n_dev, "device ordinal out of range");
+    PTB_CUDA(cudaSetDevice(device));
+
+    ptb_scene* s = new ptb_scene;
+    try {
+        s->device = device;
+        cudaDeviceProp prop{};
+        PTB_CUDA(cudaGetDeviceProperties(&prop, device));
+        s->sm_count = prop.multiProcessorCount;
+
+        // ---- meshes: AABB, KD tree, triangle records ----
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<DMesh> meshes(desc.n_meshes);
+        std::vector<uint2> nodes;
+        std::vector<uint32_t> refs;
+        std::vector<float4> tri_a, tri_ab, tri_ac;
+        std::vector<float> vpos, vnrm, vtan, vuv;
+        s->trees.resize(desc.n_meshes);
+        for (uint32_t m = 0; m < desc.n_meshes; m++) {
+            const ptb_mesh_desc& md = desc.meshes[m];
+            const Aabb box = mesh_aabb(md.positions, md.n_vertices);
+            KdTree& tree = s->trees[m];
+            build_kd_tree(md.positions, md.indices, md.n_triangles, box, desc.kd_use_sah != 0, max_depth, 0, tree);
+            require(nodes.size() + tree.nodes.size() < (1ull << 32), "KD nodes exceed 32-bit indexing");
+            require(refs.size() + tree.refs.size() < (1ull << 32), "KD leaf references exceed 32-bit indexing");
+            require(tri_a.size() + md.n_triangles < (1ull << 32), "triangles exceed 32-bit indexing");
+            DMesh& dm = meshes[m];
+            for (int a = 0; a < 3; a++) {
+                dm.aabb_min[a] = box.min[a];
+                dm.aabb_max[a] = box.max[a];
+            }
+            dm.node_base = static_cast<uint32_t>(nodes.size());
+            dm.ref_base = static_cast<uint32_t>(refs.size());
+            dm.tri_base = static_cast<uint32_t>(tri_a.size());
+            dm.vtx_base = static_cast<uint32_t>(vpos.size() / 3);
+            dm.n_triangles = md.n_triangles;
+            dm.pad = 0;
+            for (const KdNode& n : tree.nodes) nodes.push_back(make_uint2(n.w0, n.w1));
+            refs.insert(refs.end(), tree.refs.begin(), tree.refs.end());
+            for (uint32_t t = 0; t < md.n_triangles; t++) {
+                const uint32_t i0 = md.indices[3 * t], i1 = md.indices[3 * t + 1], i2 = md.indices[3 * t + 2];
+                const V3 a{md.positions[3 * i0], md.positions[3 * i0 + 1], md.positions[3 * i0 + 2]};
+                const V3 b{md.positions[3 * i1], md.positions[3 * i1 + 1], md.positions[3 * i1 + 2]};
+                const V3 c{md.positions[3 * i2], md.positions[3 * i2 + 1], md.positions[3 * i2 + 2]};
+                const V3 ab = a - b, ac = a - c; // the first two columns of triangle::intersect's matrix
+                float w0, w1, w2;
+                std::memcpy(&w0, &i0, 4);
+                std::memcpy(&w1, &i1, 4);
+                std::memcpy(&w2, &i2, 4);
+                tri_a.push_back(make_float4(a.x, a.y, a.z, w0));
+                tri_ab.push_back(make_float4(ab.x, ab.y, ab.z, w1));
+                tri_ac.push_back(make_float4(ac.x, ac.y, ac.z, w2));
+            }
+            vpos.insert(vpos.end(), md.positions, md.positions + size_t(md.n_vertices) * 3);
+            vnrm.insert(vnrm.end(), md.normals, md.normals + size_t(md.n_vertices) * 3);
+            vtan.insert(vtan.end(), md.tangents, md.tangents + size_t(md.n_vertices) * 3);
+            vuv.insert(vuv.end(), md.uvs, md.uvs + size_t(md.n_vertices) * 2);
+            s->info.n_triangles += md.n_triangles;
+            s->info.n_kd_nodes += tree.nodes.size();
+            s->info.n_kd_branches += tree.n_branches;
+            s->info.n_kd_leaves += tree.n_leaves;
+            s->info.n_leaf_refs += tree.refs.size();
+            s->info.kd_max_depth_reached = std::max(s->info.kd_max_depth_reached, tree.max_depth_reached);
+        }
+        s->info.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+        // ---- instances ----
+        std::vector<DInstance> instances(desc.n_instances);
+        for (uint32_t i = 0; i < desc.n_instances; i++) {
+            const ptb_instance_desc& id = desc.instances[i];
+            DInstance& di = instances[i];
+            di.fwd = xform_from(id.origin, id.basis);
+            di.inv = inverse(di.fwd);                         // transform::inverse, per ray in the reference
+            di.normal_mat = transpose(inverse(di.fwd.basis)); // renderer.cpp:698
+            // model::recalculate_aabb: clear() then add(min), add(max) of every surface's mesh box
+            float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {FLT_MIN, FLT_MIN, FLT_MIN};
+            for (uint32_t k = 0; k < id.n_surfaces; k++) {
+                const DMesh& dm = meshes[desc.surfaces[id.first_surface + k].mesh];
+                for (int a = 0; a < 3; a++) {
+                    mn[a] = rmin(mn[a], dm.aabb_min[a]);
+                    mx[a] = rmax(mx[a], dm.aabb_min[a]);
+                    mn[a] = rmin(mn[a], dm.aabb_max[a]);
+                    mx[a] = rmax(mx[a], dm.aabb_max[a]);
+                }
+            }
+            for (int a = 0; a < 3; a++) {
+                di.aabb_min[a] = mn[a];
+                di.aabb_max[a] = mx[a];
+            }
+            di.first_surface = id.first_surface;
+            di.n_surfaces = id.n_surfaces;
+        }
+        std::vector<DSurface> surfaces(desc.n_surfaces);
+        for (uint32_t k = 0; k < desc.n_surfaces; k++) surfaces[k] = DSurface{desc.surfaces[k].mesh, desc.surfaces[k].material};
+
+        // ---- materials and textures ----
+        std::vector<DMaterial> materials(desc.n_materials);
+        for (uint32_t m = 0; m < desc.n_materials; m++) {
+            const ptb_material_desc& md = desc.materials[m];
+            DMaterial& dm = materials[m];
+            std::memset(&dm, 0, sizeof(dm));
+            for (int c = 0; c < 3; c++) {
+                dm.albedo[c] = md.albedo[c];
+                dm.emissive[c] = md.emissive[c];
+            }
+            dm.opacity = md.opacity;
+            dm.roughness = md.roughness;
+            dm.metallic = md.metallic;
+            dm.ior = md.ior;
+            dm.shadow_catcher = md.shadow_catcher;
+            dm.normal_tex = md.normal_tex;
+            dm.albedo_tex = md.albedo_tex;
+            dm.opacity_tex = md.opacity_tex;
+            dm.roughness_tex = md.roughness_tex;
+            dm.metallic_tex = md.metallic_tex;
+            dm.emissive_tex = md.emissive_tex;
+            if (md.shadow_catcher || md.opacity_tex != PTB_NO_TEXTURE ||
+                !(md.opacity == 1.0f || std::fabs(md.opacity - 1.0f) < kEpsilon))
+                s->has_pass_through = true;
+            dm.any_tex = (md.normal_tex & md.albedo_tex & md.opacity_tex & md.roughness_tex & md.metallic_tex &
+                          md.emissive_tex) != PTB_NO_TEXTURE;
+        }
+        std::vector<DTexture> textures(desc.n_textures);
+        std::vector<unsigned char> texels;
+        for (uint32_t t = 0; t < desc.n_textures; t++) {
+            const ptb_texture_desc& td = desc.textures[t];
+            const size_t bytes = size_t(td.width) * td.height * td.channels * (td.is_float ? 4 : 1);
+            while (texels.size() % 16) texels.push_back(0);
+            textures[t] = DTexture{(unsigned long long)texels.size(), td.width, td.height, td.channels, td.is_float, td.srgb, 0};
+            const unsigned char* src = static_cast<const unsigned char*>(td.pixels);
+            texels.insert(texels.end(), src, src + bytes);
+        }
+
+        // ---- upload ----
+        auto t1 = std::chrono::steady_clock::now();
+        DScene& d = s->d;
+        d.instances = upload(s, instances);
+        d.surfaces = upload(s, surfaces);
+        d.meshes = upload(s, meshes);
+        d.kd_nodes = upload(s, nodes);
+        d.kd_refs = upload(s, refs);
+        d.tri_a = upload(s, tri_a);
+        d.tri_ab = upload(s, tri_ab);
+        d.tri_ac = upload(s, tri_ac);
+        d.vtx_pos = upload(s, vpos);
+        d.vtx_nrm = upload(s, vnrm);
+        d.vtx_tan = upload(s, vtan);
+        d.vtx_uv = upload(s, vuv);
+        d.materials = upload(s, materials);
+        d.textures = upload(s, textures);
+        d.texels = upload(s, texels);
+        d.n_instances = desc.n_instances;
+        d.camera.xf = xform_from(desc.camera.origin, desc.camera.basis);
+        d.camera.tan_half_fov = std::tan(desc.camera.yfov * 0.5F); // camera::set_fov (glibc tanf, as the reference)
+        d.sun.enabled = desc.sun.enabled ? 1 : 0;
+        if (desc.sun.enabled) {
+            const float zero[3] = {0, 0, 0};
+            const Xform sx = xform_from(zero, desc.sun.basis);
+            d.sun.direction = mul(sx.basis, V3{0.0f, 0.0f, 1.0f}); // basis * fvec3::backward
+            d.sun.energy = V3{desc.sun.energy[0], desc.sun.energy[1], desc.sun.energy[2]};
+            d.sun.angular_radius = desc.sun.angular_radius;
+        } else {
+            d.sun.direction = V3{0, 0, 1};
+            d.sun.energy = V3{0, 0, 0};
+            d.sun.angular_radius = 0;
+        }
+        d.environment = V3{desc.environment_factor[0], desc.environment_factor[1], desc.environment_factor[2]};
+        d.transparent_background = desc.transparent_background ? 1 : 0;
+        PTB_CUDA(cudaDeviceSynchronize());
+        s->info.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+        s->info.n_instances = desc.n_instances;
+        s->info.n_surfaces = desc.n_surfaces;
+        s->info.n_meshes = desc.n_meshes;
+        s->info.n_materials = desc.n_materials;
+        s->info.n_textures = desc.n_textures;
+    } catch (...) {
+        destroy_scene(s);
+        throw;
+    }
+    return s;
+}
+
+} // namespace ptb

@@ -1,0 +1,312 @@
+/*
+ * ptb.h — C ABI of the B200-native path-tracing hot path (libptb.so).
+ *
+ * This is the drop-in boundary for the one hot path of
+ * vmanam0451/distributed-path-tracer: KD-tree traversal, ray/triangle
+ * intersection and the Monte-Carlo integrator.  The reference has no FFI seam
+ * for this path (it is statically linked, path-tracer-core/CMakeLists.txt:25,41-44),
+ * so every entry point below names the reference C++ interface it replaces.
+ * All paths in the comments are relative to the reference repository root;
+ * LIB/ = path-tracer-core/path_tracer_lib/path_tracer/, APP/ = path-tracer-core/src/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary
+ *   - every function returns a ptb_status; nothing throws, nothing aborts
+ *   - ptb_last_error() returns a thread-local, human-readable message
+ *   - scene handles are immutable after creation and may be shared by threads
+ *   - output buffers are caller-owned HOST memory unless the name ends in _dev
+ *   - the library FAILS (PTB_E_CUDA) when no CUDA device is usable: there is
+ *     no CPU fallback of any kind
+ */
+#ifndef PTB_H
+#define PTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_ABI_VERSION 1
+
+typedef enum ptb_status {
+    PTB_OK = 0,
+    PTB_E_INVALID = 1, /* bad argument / malformed scene description        */
+    PTB_E_CUDA = 2,    /* CUDA runtime error, or no usable device            */
+    PTB_E_NCCL = 3,    /* reserved for the multi-GPU context                 */
+    PTB_E_OOM = 4,     /* host or device allocation failed                   */
+    PTB_E_IO = 5       /* file missing / unreadable / malformed glTF         */
+} ptb_status;
+
+/* ---------------------------------------------------------------- scene -- */
+
+/* One triangle mesh = one glTF primitive = one reference core::mesh
+ * (LIB/core/mesh.hpp:13-37; vertex layout LIB/core/vertex.hpp:7-12). */
+typedef struct ptb_mesh_desc {
+    const float* positions;  /* n_vertices * 3                               */
+    const float* normals;    /* n_vertices * 3                               */
+    const float* tangents;   /* n_vertices * 3 (the reference reads xyz only,
+                                LIB/core/renderer.cpp:215-218,248-250)        */
+    const float* uvs;        /* n_vertices * 2                               */
+    uint32_t n_vertices;
+    const uint32_t* indices; /* n_triangles * 3                              */
+    uint32_t n_triangles;
+} ptb_mesh_desc;
+
+/* scene::model::surface = {mesh, material} (LIB/scene/model.hpp:15-18). */
+typedef struct ptb_surface_desc {
+    uint32_t mesh;
+    uint32_t material;
+} ptb_surface_desc;
+
+/* One entity carrying a scene::model, with its GLOBAL transform
+ * (LIB/scene/transform.hpp:14-15: origin + column-major 3x3 basis, columns
+ * x,y,z).  Instances are intersected in array order with strict '<' on world
+ * distance, i.e. the first one wins a tie — the array order therefore has to
+ * be the visiting order of renderer::intersect (LIB/core/renderer.cpp:645-671).
+ * Several instances may name the same surface range (instancing). */
+typedef struct ptb_instance_desc {
+    float origin[3];
+    float basis[9]; /* x.x x.y x.z  y.x y.y y.z  z.x z.y z.z                 */
+    uint32_t first_surface;
+    uint32_t n_surfaces;
+} ptb_instance_desc;
+
+/* An 8-bit or float texture (LIB/image/image.hpp, image_texture.cpp:21-62).
+ * `srgb` makes reads of channels 0..2 decode with pow(v, 2.2)
+ * (LIB/image/image.cpp:124-141). */
+typedef struct ptb_texture_desc {
+    const void* pixels; /* row-major, `channels` interleaved                 */
+    uint32_t width, height, channels;
+    uint32_t is_float; /* 0: uint8 (value/255), 1: float32                   */
+    uint32_t srgb;
+} ptb_texture_desc;
+
+#define PTB_NO_TEXTURE 0xFFFFFFFFu
+
+/* core::material (LIB/core/material.hpp:9-41, getters material.cpp:6-53). */
+typedef struct ptb_material_desc {
+    float albedo[3];
+    float opacity;
+    float roughness;
+    float metallic;
+    float emissive[3];
+    float ior; /* 1.33 in the reference (material.hpp:16)                    */
+    uint32_t shadow_catcher;
+    uint32_t normal_tex, albedo_tex, opacity_tex, roughness_tex, metallic_tex,
+        emissive_tex; /* PTB_NO_TEXTURE when absent                          */
+} ptb_material_desc;
+
+/* scene::camera on an entity (LIB/scene/camera.cpp:10-30): global transform
+ * and vertical field of view in radians. */
+typedef struct ptb_camera_desc {
+    float origin[3];
+    float basis[9];
+    float yfov;
+} ptb_camera_desc;
+
+/* scene::sun_light (LIB/scene/sun_light.hpp:7-11) with the global basis of
+ * its entity (LIB/core/renderer.cpp:499). */
+typedef struct ptb_sun_desc {
+    uint32_t enabled;
+    float basis[9];
+    float energy[3];
+    float angular_radius;
+} ptb_sun_desc;
+
+typedef struct ptb_scene_desc {
+    const ptb_mesh_desc* meshes;
+    uint32_t n_meshes;
+    const ptb_surface_desc* surfaces;
+    uint32_t n_surfaces;
+    const ptb_instance_desc* instances;
+    uint32_t n_instances;
+    const ptb_material_desc* materials;
+    uint32_t n_materials;
+    const ptb_texture_desc* textures;
+    uint32_t n_textures;
+    ptb_camera_desc camera;
+    ptb_sun_desc sun;
+    float environment_factor[3];    /* renderer.hpp:29                       */
+    uint32_t transparent_background; /* renderer.hpp:30                      */
+    uint32_t kd_use_sah;  /* mesh::build_kd_tree(use_sah=true, ...)          */
+    uint32_t kd_max_depth; /* ... max_depth=25  (LIB/core/mesh.hpp:34); 0 → 25 */
+} ptb_scene_desc;
+
+typedef struct ptb_scene ptb_scene;
+
+/* Replaces renderer::get_mesh + mesh::recalculate_aabb + mesh::build_kd_tree
+ * (LIB/core/renderer.cpp:177-263, LIB/core/mesh.cpp:254-298): builds, on the
+ * host, the identical SAH KD-tree per mesh, flattens it and uploads triangles,
+ * nodes, leaf references, vertex attributes, materials and textures to HBM on
+ * `device`. */
+ptb_status ptb_scene_create(const ptb_scene_desc* desc, int device, ptb_scene** out);
+
+/* Replaces renderer::load_gltf (LIB/core/renderer.cpp:61-99, process_node
+ * :101-174): camera and sun light are matched by name, `camera_index` and
+ * `sun_light_index` as renderer.hpp:31-32 (0xFFFFFFFF = renderer::no_sun_light). */
+ptb_status ptb_scene_load_gltf(const char* path, uint32_t camera_index,
+                               uint32_t sun_light_index, int device, ptb_scene** out);
+
+void ptb_scene_destroy(ptb_scene* scene);
+
+typedef struct ptb_scene_info {
+    uint32_t n_instances, n_surfaces, n_meshes, n_materials, n_textures;
+    uint64_t n_triangles;   /* unique triangles over all meshes              */
+    uint64_t n_kd_nodes;    /* flattened nodes (branches + leaves)           */
+    uint64_t n_kd_branches;
+    uint64_t n_kd_leaves;
+    uint64_t n_leaf_refs;   /* triangle references held by leaves            */
+    uint32_t kd_max_depth_reached;
+    uint64_t device_bytes;  /* HBM held by the scene                         */
+    double build_seconds;   /* host KD build                                 */
+    double upload_seconds;
+} ptb_scene_info;
+
+ptb_status ptb_scene_get_info(const ptb_scene* scene, ptb_scene_info* out);
+
+/* Test hook for row K of the scope table: serialises the host-built tree of
+ * one mesh in depth-first order so that it can be compared with the
+ * reference's pointer tree.  Record stream (uint32 words):
+ *   branch: 0x80000000|axis, split-bits, has_left, has_right  then left, right
+ *   leaf:   count, idx[count]
+ * Call with words == NULL to obtain the required length. */
+ptb_status ptb_scene_dump_kd(const ptb_scene* scene, uint32_t mesh, uint32_t* words,
+                             uint64_t capacity, uint64_t* n_words);
+
+/* ------------------------------------------------------------- hot path -- */
+
+typedef struct ptb_hit {
+    uint32_t instance; /* 0xFFFFFFFF = miss                                   */
+    uint32_t surface;  /* ordinal inside the instance's surface list          */
+    uint32_t triangle; /* index into the mesh's triangle list                 */
+    float t;           /* world-space distance (LIB/scene/model.cpp:62-63)    */
+    float bary[3];     /* (alpha, beta, gamma), triangle.cpp:185-189          */
+} ptb_hit;
+
+#define PTB_MISS 0xFFFFFFFFu
+
+/* Closest hit for an explicit ray set: replaces renderer::intersect's search
+ * (LIB/core/renderer.cpp:645-675 → LIB/scene/model.cpp:20-72 →
+ * LIB/core/mesh.cpp:300-405 → LIB/geometry/triangle.cpp:120-190).
+ * `origin_dir` is n * 6 floats (origin xyz, direction xyz); directions are
+ * normalised on the way in exactly as geometry::ray's constructor does
+ * (LIB/geometry/ray.cpp:6-8).  Triangle ids are bit-exact with the reference. */
+ptb_status ptb_trace_rays(const ptb_scene* scene, const float* origin_dir, uint64_t n,
+                          ptb_hit* hits_out);
+
+/* Full intersect_result for an explicit ray set (renderer.cpp:688-724): world
+ * position(3), uv(2), interpolated normal(3), tangent(3), shading normal(3)
+ * = 14 floats per ray, zeros on a miss.  `attrs_out` may be NULL. */
+ptb_status ptb_trace_rays_attrs(const ptb_scene* scene, const float* origin_dir, uint64_t n,
+                                ptb_hit* hits_out, float* attrs_out);
+
+typedef enum ptb_integrator {
+    /* core::renderer::trace, fixed depth, no Russian roulette
+     * (LIB/core/renderer.cpp:437-643) */
+    PTB_INTEGRATOR_LIB = 0,
+    /* processors::worker::trace_iter, throughput clamp + Russian roulette
+     * (APP/processors/worker/worker.cpp:285-514) */
+    PTB_INTEGRATOR_APP_RR = 1
+} ptb_integrator;
+
+/* The worker's render request.  The reference request is
+ * {samples, bounces, X, Y} (APP/models/work_info.hpp:27-30) over the whole
+ * frame; tile rectangle, seed and first sample index are extensions that let
+ * tiles and sample ranges be sharded across GPUs. */
+typedef struct ptb_tile_req {
+    uint32_t full_w, full_h; /* X, Y                                          */
+    uint32_t x0, y0, w, h;   /* tile rectangle inside the frame               */
+    uint32_t spp;            /* samples                                       */
+    uint32_t max_depth;      /* bounces                                       */
+    uint64_t seed;           /* Philox key                                    */
+    uint32_t first_sample;   /* index of this call's first sample (0 normally)*/
+    uint32_t integrator;     /* ptb_integrator                                */
+    uint32_t first_sample_unjittered; /* APP/processors/worker/worker.cpp:125-129 */
+    uint32_t reserved;
+} ptb_tile_req;
+
+typedef struct ptb_render_stats {
+    uint64_t paths;         /* camera paths started                           */
+    uint64_t rays;          /* scene-level intersect calls: primary + bounce
+                               + shadow, counted by the extend/shadow kernels */
+    uint64_t kernel_launches;
+    double gpu_seconds;     /* CUDA-event time of the whole render            */
+    double extend_seconds;  /* closest-hit + shadow kernels                   */
+    double shade_seconds;   /* ray-gen + shade + accumulate kernels           */
+    uint64_t extend_launches;
+    uint64_t node_visits, leaf_visits, tri_tests; /* only when the scene was
+                               created with counters enabled (ptb_set_option) */
+} ptb_render_stats;
+
+/* Replaces renderer::render (LIB/core/renderer.cpp:334-428) /
+ * worker::run's pipeline (APP/processors/worker/worker.cpp:25-105) for one
+ * tile: linear running-mean radiance, row-major w*h*3, and the alpha channel
+ * (w*h, may be NULL). Synchronous. */
+ptb_status ptb_render_tile(const ptb_scene* scene, const ptb_tile_req* req, float* rgb_out,
+                           float* alpha_out, ptb_render_stats* stats_out);
+
+/* Same, leaving the result in device memory: `rgba_dev` is a device pointer
+ * to w*h float4 (rgb = mean radiance, a = alpha).  `stream` is a cudaStream_t
+ * (NULL = the default stream).  Asynchronous with respect to the host except
+ * for the per-bounce queue-size read-back. */
+ptb_status ptb_render_tile_dev(const ptb_scene* scene, const ptb_tile_req* req, void* rgba_dev,
+                               void* stream, ptb_render_stats* stats_out);
+
+/* tonemap_approx_aces (LIB/core/utils.hpp:29-36) + image::write's sRGB
+ * encode and rounding (LIB/image/image.cpp:143-154): n pixels of linear rgb
+ * (+ alpha, may be NULL → 1) to RGBA8, on the GPU. */
+ptb_status ptb_tonemap_rgba8(const float* rgb, const float* alpha, uint64_t n_pixels,
+                             uint8_t* rgba8_out);
+
+/* image::save_to_memory_png (LIB/image/image.cpp:111-122): RGBA8 → PNG file. */
+ptb_status ptb_write_png(const char* path, const uint8_t* rgba8, uint32_t w, uint32_t h);
+
+/* ------------------------------------------------- host-only / test hooks -- */
+
+/* The build step of ptb_scene_create alone, on the host, without CUDA:
+ * mesh::recalculate_aabb + mesh::build_kd_tree (LIB/core/mesh.cpp:254-298)
+ * serialised as ptb_scene_dump_kd does.  Lets the tree-identity tests run on
+ * a machine without a GPU.  aabb6_out (min xyz, max xyz) may be NULL. */
+ptb_status ptb_host_build_kd(const float* positions, uint32_t n_vertices, const uint32_t* indices,
+                             uint32_t n_triangles, uint32_t use_sah, uint32_t max_depth, int threads,
+                             uint32_t* words, uint64_t capacity, uint64_t* n_words, float* aabb6_out);
+
+/* renderer::load_gltf's parsing half, host-only: glTF → scene description
+ * (instances in renderer::intersect visiting order). */
+typedef struct ptb_desc ptb_desc;
+ptb_status ptb_desc_load_gltf(const char* path, uint32_t camera_index, uint32_t sun_light_index,
+                              ptb_desc** out);
+const ptb_scene_desc* ptb_desc_get(const ptb_desc* desc);
+void ptb_desc_free(ptb_desc* desc);
+
+/* Primary rays exactly as renderer::render builds them (renderer.cpp:360-370 →
+ * camera::get_ray) for caller-supplied pixel coordinates and jitter (aa = 2
+ * floats per ray): the device ray-gen function, exposed so that it can be
+ * compared bit for bit.  origin_dir_out: n * 6 floats. */
+ptb_status ptb_camera_rays(const ptb_scene* scene, uint32_t w, uint32_t h, const uint32_t* px,
+                           const uint32_t* py, const float* aa, uint64_t n, float* origin_dir_out);
+
+/* ptb_trace_rays plus CUDA-event timing of the extend kernel and, with the
+ * "count_visits" option, the node / leaf / triangle visit counters. */
+ptb_status ptb_trace_rays_stats(const ptb_scene* scene, const float* origin_dir, uint64_t n,
+                                ptb_hit* hits_out, ptb_render_stats* stats_out);
+
+/* Registers per thread of the extend kernel as loaded (cudaFuncGetAttributes). */
+int ptb_extend_registers(void);
+
+/* ----------------------------------------------------------------- misc -- */
+
+/* Options: "wave_paths" (paths per wavefront), "count_visits" (0/1),
+ * "extend_blocks_per_sm", "sort_rays" (0/1). Unknown names → PTB_E_INVALID. */
+ptb_status ptb_set_option(const char* name, int64_t value);
+
+const char* ptb_last_error(void);
+int ptb_abi_version(void);
+int ptb_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB_H */
