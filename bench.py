@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ptb|reference] [--config c2|c1|c3]
+
+Metric (BASELINE.json): Mrays/s (primary + bounce + shadow rays, counted by the extend/shadow kernels)
+on the named configuration; 1080p@64spp frames/s is reported inside `config`.
+
+A "step" is one pass of the hot path over one frame of synthetic input:
+  * N = 1: configs[1] of BASELINE.json — the synthetic 999 698-triangle procedural heightfield,
+    1920x1080, 64 spp, depth 4 (reference library default), integrator = renderer::trace semantics;
+  * N > 1 (torchrun, one rank per GPU): the same frame at 64*N spp, cut into 8*N tiles that the ranks
+    claim from a shared counter (work stealing); per-GPU work is therefore fixed → "scaling": "weak".
+    The render has no collective; the framebuffer gather (reduce of disjoint tiles onto rank 0 over
+    NCCL) belongs to the end-to-end figure only.
+`value` is timed with CUDA events on the launching stream with the scene resident in HBM, barrier +
+synchronize on both sides, max over ranks.  `e2e` goes through the public host call
+(cluster.render_frame → libptb C ABI) and includes the request upload, the framebuffer gather and the
+device→host copy of the finished frame into pinned memory.
+
+`--impl reference` times the reference's own CPU renderer (oracle/_ref, the unmodified library compiled
+from /root/reference by oracle/Makefile; the plain-C port oracle/pt_oracle.c if that is absent) on the
+box's host cores on a bounded sample of the same workload.  This file is the only place outside tests/
+and __graft_entry__.smoke() that touches oracle/, and only for that leg and the `cpu_baseline` object.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # name: (description, full_w, full_h, spp, depth, integrator)
+    "c1": ("C1 cornell-box 256x256 16spp depth4 LIB", 256, 256, 16, 4, 0),
+    "c2": ("C2 heightfield 999698 tris 1920x1080 64spp depth4 LIB", 1920, 1080, 64, 4, 0),
+    "c3": ("C3 cornell-box 1920x1080 256spp depth16 APP_RR", 1920, 1080, 256, 16, 1),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_description(cfg_name, n_grid):
+    import ptb200 as ptb
+    from ptb200 import procedural as P
+    if cfg_name == "c2":
+        return P.heightfield_scene(n_grid)
+    return ptb.load_gltf_description(P.cornell_gltf_path())
+
+
+# ------------------------------------------------------------------ reference arm / CPU baseline ----
+
+def cpu_reference(cfg_name, n_grid, depth, integrator, sample_seconds=15.0, steps=1, warmup=0):
+    """Times the reference CPU renderer on a bounded sample of the workload.  → dict for `cpu_baseline`
+    plus per-step values.  kind = "reference" (oracle/_ref) or "port" (oracle/pt_oracle.c)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reflib
+    desc = build_description(cfg_name, n_grid)
+    flat = reflib.FlatScene(desc.meshes, desc.surfaces, desc.instances, desc.materials, desc.camera, desc.sun,
+                            desc.environment_factor, desc.transparent_background)
+    cores = os.cpu_count() or 1
+    full_w, full_h = CONFIGS[cfg_name][1], CONFIGS[cfg_name][2]
+    t0 = time.perf_counter()
+    if reflib.available():
+        kind = "reference"
+        scene = reflib.RefScene.from_flat(flat)
+        threads = reflib.hardware_threads()
+    else:
+        import portlib
+        kind = "port"
+        scene = portlib.PortScene(flat)
+        threads = cores
+    build_s = time.perf_counter() - t0
+    # rays per path of this workload (restated integrator that counts scene-level intersect calls)
+    pw, ph = max(16, full_w // 8), max(9, full_h // 8)
+    mode_count = 1 if integrator == 1 else (2 if kind == "reference" else 0)
+    _, _, rays, _ = scene.render_linear(pw, ph, 2, depth, mode=mode_count, threads=threads)
+    rays_per_path = rays / float(pw * ph * 2)
+    # calibrate the sample so that one step is about sample_seconds of CPU wall time
+    sw, sh = max(32, full_w // 4), max(18, full_h // 4)
+
+    def one(spp):
+        if kind == "reference" and integrator == 0:
+            _, secs = scene.render_png(sw, sh, spp, depth, threads=0)  # the reference's own render()
+        else:
+            _, _, _, secs = scene.render_linear(sw, sh, spp, depth, mode=(1 if integrator == 1 else 0), threads=threads)
+        return secs
+
+    probe = one(1)
+    spp = int(max(1, min(64, round(sample_seconds / max(probe, 1e-3)))))
+    values, secs_all = [], []
+    for i in range(warmup + steps):
+        secs = one(spp)
+        if i >= warmup:
+            secs_all.append(secs)
+            values.append(sw * sh * spp * rays_per_path / secs / 1e6)
+    sample = (f"{sw}x{sh} x {spp} spp of the same scene and camera, depth {depth}, "
+              f"{'renderer::render()' if (kind == 'reference' and integrator == 0) else 'trace_iter restated over the library' if kind == 'reference' else 'plain-C port'}"
+              f" on {threads} threads; rays/path {rays_per_path:.3f} counted on a {pw}x{ph}x2 pass; "
+              f"scene build {build_s:.1f} s not timed")
+    return dict(value=float(np.mean(values)), unit="Mrays/s", cores=int(threads), kind=kind, sample=sample,
+                ms_per_step=float(np.mean(secs_all) * 1e3), paths_per_s=float(sw * sh * spp / np.mean(secs_all)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    desc_name, full_w, full_h, spp, depth, integ = CONFIGS[args.config]
+    r = cpu_reference(args.config, args.n_grid, depth, integ, sample_seconds=args.cpu_seconds, steps=args.steps,
+                      warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc_name, "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------ product arm ----
+
+def run_ptb(args):
+    import torch
+    import torch.distributed as dist
+    import ptb200 as ptb
+    from ptb200 import cluster
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    device_index = torch.cuda.current_device()
+
+    desc_name, full_w, full_h, spp0, depth, integ = CONFIGS[args.config]
+    if args.spp:
+        spp0 = args.spp
+    spp = spp0 * world  # weak scaling: 64 spp per GPU
+    t_build = time.perf_counter()
+    desc = build_description(args.config, args.n_grid)
+    scene = ptb.Scene.create(desc, device_index)
+    info = scene.info()
+    t_build = time.perf_counter() - t_build
+    ptb.set_option("wave_paths", args.wave_paths)
+
+    cols, rows = cluster.tile_grid_for(world, args.tiles_per_gpu)
+    tiles = cluster.make_tiles(full_w, full_h, cols, rows)
+    frame = torch.zeros((full_h, full_w, 4), dtype=torch.float32, device=dev)
+    tile_buf = torch.zeros(max(t[2] * t[3] for t in tiles) * 4, dtype=torch.float32, device=dev)
+    pinned = torch.empty((full_h, full_w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
+    stream = torch.cuda.current_stream()
+
+    def render_tile(tile, out_frame, seed, stats=True):
+        x0, y0, w, h = tile
+        st = scene.render_tile_dev(tile_buf.data_ptr(), full_w, full_h, spp, depth, tile=tile, seed=seed,
+                                   integrator=integ, stream=stream.cuda_stream, want_stats=stats)
+        out_frame[y0:y0 + h, x0:x0 + w, :] = tile_buf[: w * h * 4].view(h, w, 4)
+        return st
+
+    epoch = [0]
+
+    def step(seed, gather):
+        frame.zero_()
+        epoch[0] += 1
+        return cluster.render_frame(full_w, full_h, tiles, lambda t, f: render_tile(t, f, seed), frame,
+                                    epoch=epoch[0], gather=gather)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step(1000 + i, gather=True)
+    barrier()
+
+    # ---- timed region: kernel throughput, results stay in HBM
+    sampler = ClockSampler(device_index)
+    if rank == 0:
+        sampler.start()
+    rays = paths = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_total = 0.0
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations
+        barrier()
+        ev0.record(stream)
+        r = step(1 + i, gather=False)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        ms_total += cluster.all_max([ms], dev)[0]
+        rays += r["rays"]
+        paths += r["paths"]
+    rays_all, paths_all = cluster.all_sum([rays, paths], dev)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = rays_all / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end: public host call, request in, finished frame in pinned host memory on rank 0
+    e2e_ms = 0.0
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        r = step(1 + i, gather=True)
+        if rank == 0:
+            pinned.copy_(frame, non_blocking=True)
+        barrier()
+        e2e_ms += cluster.all_max([(time.perf_counter() - t0) * 1e3], dev)[0]
+    e2e_value = rays_all / (e2e_ms * 1e-3) / 1e6
+    n_tiles_rank = len(tiles) / world
+    h2d = int(ctypes.sizeof(ptb.TileReq) * len(tiles))
+    d2h = int(full_w * full_h * 16)
+
+    # ---- roofline of the dominant kernel (extend): separate, untimed-for-`value` passes on rank 0's share
+    hbm_peak, peak_src = load_peaks()
+    roofline = None
+    if rank == 0:
+        ptb.set_option("time_stages", 1)
+        st_t = [render_tile(t, frame, 1, stats=True) for t in tiles[:: world]]
+        ptb.set_option("time_stages", 0)
+        ptb.set_option("count_visits", 1)
+        st_c = [render_tile(t, frame, 1, stats=True) for t in tiles[:: world]]
+        ptb.set_option("count_visits", 0)
+        ext_s = sum(s["extend_seconds"] for s in st_t)
+        shade_s = sum(s["shade_seconds"] for s in st_t)
+        ext_launches = sum(s["extend_launches"] for s in st_t)
+        n_rays = sum(s["rays"] for s in st_c)
+        nb, nl, nt = (sum(s[k] for s in st_c) for k in ("node_visits", "leaf_visits", "tri_tests"))
+        alg_bytes = 32 * n_rays + 8 * nb + 8 * nl + (4 + 48) * nt + 32 * n_rays
+        achieved = alg_bytes / ext_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "extend_kernel", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_ray": alg_bytes / max(n_rays, 1), "rays_per_launch": n_rays / max(ext_launches, 1),
+                    "avg_launch_ms": ext_s / max(ext_launches, 1) * 1e3,
+                    "extend_share_of_step": ext_s / max(ext_s + shade_s, 1e-12),
+                    "visits_per_ray": {"branch": nb / max(n_rays, 1), "leaf": nl / max(n_rays, 1),
+                                       "tri": nt / max(n_rays, 1)},
+                    "extend_Mrays_per_s": n_rays / ext_s / 1e6}
+        prof = os.path.join(ROOT, "profiles", "extend_traffic.json")
+        if os.path.exists(prof):
+            try:
+                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    # ---- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        c = cpu_reference(args.config, args.n_grid, depth, integ, sample_seconds=args.cpu_seconds)
+        cpu = {"value": c["value"], "unit": "Mrays/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
+
+    if rank == 0:
+        frames_per_s = world * 1e3 / ms_per_step  # 64-spp-equivalent frames
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc_name + (f", {spp} spp total ({spp0}/GPU)" if world > 1 else ""),
+                       "triangles": int(info["n_triangles"]), "kd_nodes": int(info["n_kd_nodes"]),
+                       "kd_leaf_refs": int(info["n_leaf_refs"]), "scene_bytes": int(info["device_bytes"]),
+                       "kd_build_s": info["build_seconds"], "tiles": f"{cols}x{rows} work-stolen",
+                       "parallelism": f"tiles x{world}", "wave_paths": args.wave_paths,
+                       "frames_per_s_1080p64": frames_per_s if args.config == "c2" else None,
+                       "rays_per_path": rays_all / max(paths_all, 1),
+                       "l2": "256 MiB buffer written between timed iterations; scene + path state exceed L2"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_total(tiles, spp, depth, args.wave_paths, args.steps)),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def launches_total(tiles, spp, depth, wave_paths, steps):
+    """Kernels of libptb launched inside the timed region: per wave 1 raygen + depth x (extend + shade)
+    + 1 accumulate (same arithmetic as render.cu; ptb_render_stats.kernel_launches reports it per call)."""
+    total = 0
+    for (_, _, w, h) in tiles:
+        padded = ((w + 7) // 8) * ((h + 3) // 4) * 32
+        wave_samples = max(1, min(spp, wave_paths // padded))
+        waves = (spp + wave_samples - 1) // wave_samples
+        total += waves * (2 + 2 * depth)
+    return total * steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ptb", choices=["ptb", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--n-grid", type=int, default=707, help="heightfield grid (707 → 999 698 triangles)")
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
+    ap.add_argument("--tiles-per-gpu", type=int, default=8)
+    ap.add_argument("--wave-paths", type=int, default=8 << 20)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ptb(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,204 @@
+"""Tile-sharded rendering across GPUs: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The reference distributes by GEOMETRY (every worker holds a subset of the primitives and every ray is
+meant to visit all workers, ``src/processors/worker/intersection_worker.cpp:78-110``; the transport was
+never written).  With 180 GB of HBM the scene is simply replicated and the IMAGE is sharded instead:
+
+* every rank builds/loads the same scene (or rank 0 broadcasts the description: :func:`broadcast_description`);
+* the frame is cut into tiles; ranks claim tiles from one shared counter (work stealing through the
+  ``torch.distributed`` store's atomic ``add`` — a tile takes milliseconds to seconds, a claim ~0.1 ms);
+* a tile never needs another rank's data, so the render itself has NO collective;
+* the only exchange step is the framebuffer return: tiles are disjoint, so a ``reduce(SUM)`` of the
+  zero-initialised per-rank frames onto rank 0 IS the gather (NCCL over NVLink; gloo on CPU in the tests).
+
+The module is renderer-agnostic: ``render_tile_fn(tile, out_frame)`` does the work, which lets the CPU
+test-suite drive the scheduling / merge logic with world_size 2 on gloo and a fake renderer.
+"""
+from __future__ import annotations
+
+import time
+from typing import Callable, List, Sequence, Tuple
+
+import numpy as np
+
+Tile = Tuple[int, int, int, int]  # x0, y0, w, h
+
+
+def make_tiles(full_w: int, full_h: int, cols: int, rows: int) -> List[Tile]:
+    """Row-major grid of cols x rows tiles covering the frame exactly (edges absorb the remainder)."""
+    if cols < 1 or rows < 1 or cols > full_w or rows > full_h:
+        raise ValueError("bad tile grid")
+    xs = [full_w * i // cols for i in range(cols + 1)]
+    ys = [full_h * j // rows for j in range(rows + 1)]
+    return [(xs[i], ys[j], xs[i + 1] - xs[i], ys[j + 1] - ys[j]) for j in range(rows) for i in range(cols)]
+
+
+def tile_grid_for(world_size: int, tiles_per_rank: int = 8) -> Tuple[int, int]:
+    """cols x rows with cols*rows == tiles_per_rank * world_size, as square as powers of two allow."""
+    n = max(1, tiles_per_rank * world_size)
+    cols = 1
+    while cols * cols < n:
+        cols *= 2
+    rows = max(1, n // cols)
+    if cols * rows < n:
+        rows += 1
+    return cols, rows
+
+
+class TileCounter:
+    """Work-stealing tile queue: one shared counter, atomic fetch-add.
+
+    With ``torch.distributed`` initialised the counter lives in the default process group's store
+    (``store.add`` is atomic across ranks); without it (single process) it is a plain integer."""
+
+    def __init__(self, n_tiles: int, key: str = "ptb_tile_counter", group_store=None):
+        self.n = n_tiles
+        self.key = key
+        self.store = group_store
+        self.local = 0
+
+    def next(self) -> int:
+        """Index of the next unclaimed tile, or -1 when the frame is exhausted."""
+        if self.store is None:
+            i = self.local
+            self.local += 1
+        else:
+            i = self.store.add(self.key, 1) - 1
+        return i if i < self.n else -1
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def _default_store():
+    import torch.distributed as dist
+    try:
+        return dist.distributed_c10d._get_default_store()
+    except Exception:  # pragma: no cover - very old / very new torch
+        return None
+
+
+def render_frame(full_w: int, full_h: int, tiles: Sequence[Tile],
+                 render_tile_fn: Callable[[Tile, "object"], dict | None], frame, *, epoch: int = 0,
+                 static_assignment: bool = False, gather: bool = True):
+    """Renders the tiles this rank claims into ``frame`` and gathers the full frame on rank 0.
+
+    frame: a zero-initialised torch tensor [full_h, full_w, C] (device memory under NCCL, CPU under gloo);
+           tiles this rank did not render stay zero.
+    render_tile_fn(tile, frame) renders one tile into frame[y0:y0+h, x0:x0+w] and may return a stats dict
+           (its "rays" and "paths" entries are summed).
+    epoch: distinguishes successive frames in the store (a new counter key per frame).
+    Returns dict(rays, paths, tiles=[indices this rank rendered], seconds_render, seconds_gather).
+    """
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    store = _default_store() if (dist and not static_assignment) else None
+    counter = TileCounter(len(tiles), key=f"ptb_tiles_{epoch}", group_store=store)
+    done, rays, paths = [], 0, 0
+    t0 = time.perf_counter()
+    if static_assignment or (dist and store is None):
+        mine = range(rank, len(tiles), world)  # round-robin fallback: no stealing
+        for i in mine:
+            st = render_tile_fn(tiles[i], frame)
+            done.append(i)
+            if st:
+                rays += int(st.get("rays", 0))
+                paths += int(st.get("paths", 0))
+    else:
+        while True:
+            i = counter.next()
+            if i < 0:
+                break
+            st = render_tile_fn(tiles[i], frame)
+            done.append(i)
+            if st:
+                rays += int(st.get("rays", 0))
+                paths += int(st.get("paths", 0))
+    t1 = time.perf_counter()
+    if dist and gather and world > 1:
+        # disjoint tiles + zero elsewhere: SUM onto rank 0 is the gather of the framebuffer
+        dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
+    t2 = time.perf_counter()
+    return dict(rays=rays, paths=paths, tiles=done, seconds_render=t1 - t0, seconds_gather=t2 - t1)
+
+
+def all_sum(values: Sequence[float], device=None) -> List[float]:
+    """Sum of per-rank scalars over all ranks (ray / path counters)."""
+    dist = _dist()
+    if not dist or dist.get_world_size() == 1:
+        return [float(v) for v in values]
+    import torch
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.cpu()]
+
+
+def all_max(values: Sequence[float], device=None) -> List[float]:
+    """Max over ranks (timings are reported as the slowest rank's)."""
+    dist = _dist()
+    if not dist or dist.get_world_size() == 1:
+        return [float(v) for v in values]
+    import torch
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def broadcast_description(desc, src: int = 0):
+    """Scene replication: rank ``src`` sends the flat description, every rank then builds the same
+    KD trees locally (deterministic) and uploads them.  Array payloads go through ``broadcast`` as
+    byte tensors (NCCL when the group is NCCL); the small structure goes through ``broadcast_object_list``."""
+    dist = _dist()
+    if not dist or dist.get_world_size() == 1:
+        return desc
+    import torch
+    from . import SceneDescription
+    rank = dist.get_rank()
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    if rank == src:
+        arrays, meta_meshes = [], []
+        for m in desc.meshes:
+            entry = {}
+            for k in ("positions", "normals", "tangents", "uvs", "indices"):
+                entry[k] = (m[k].shape, str(m[k].dtype))
+                arrays.append(m[k])
+            meta_meshes.append(entry)
+        meta = dict(meshes=meta_meshes, surfaces=desc.surfaces.tolist(),
+                    instances=[(o.tolist(), b.tolist(), f, c) for (o, b, f, c) in desc.instances],
+                    materials=desc.materials, camera=(desc.camera[0].tolist(), desc.camera[1].tolist(), desc.camera[2]),
+                    sun=None if desc.sun is None else tuple(np.asarray(x).tolist() if i < 2 else x
+                                                            for i, x in enumerate(desc.sun)),
+                    environment_factor=desc.environment_factor, transparent_background=desc.transparent_background,
+                    kd_use_sah=desc.kd_use_sah, kd_max_depth=desc.kd_max_depth,
+                    textures=[(t["pixels"].shape, str(t["pixels"].dtype), bool(t.get("srgb", False)))
+                              for t in desc.textures])
+        arrays += [np.ascontiguousarray(t["pixels"]) for t in desc.textures]
+        box = [meta]
+    else:
+        arrays, box = None, [None]
+    dist.broadcast_object_list(box, src=src)
+    meta = box[0]
+    shapes = [v for m in meta["meshes"] for v in (m[k] for k in ("positions", "normals", "tangents", "uvs", "indices"))]
+    shapes += [(s, d) for (s, d, _) in meta["textures"]]
+    out_arrays = []
+    for i, (shape, dtype) in enumerate(shapes):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if rank == src:
+            t = torch.from_numpy(np.ascontiguousarray(arrays[i]).view(np.uint8).reshape(-1).copy()).to(dev)
+        else:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if nbytes:
+            dist.broadcast(t, src=src)
+        out_arrays.append(t.cpu().numpy().view(dtype).reshape(shape))
+    if rank == src:
+        return desc
+    it = iter(out_arrays)
+    meshes = [{k: next(it) for k in ("positions", "normals", "tangents", "uvs", "indices")} for _ in meta["meshes"]]
+    textures = [dict(pixels=next(it), srgb=srgb) for (_, _, srgb) in meta["textures"]]
+    return SceneDescription(meshes, np.array(meta["surfaces"], np.uint32).reshape(-1, 2), meta["instances"],
+                            meta["materials"], meta["camera"], meta["sun"], meta["environment_factor"],
+                            meta["transparent_background"], meta["kd_use_sah"], meta["kd_max_depth"], textures)

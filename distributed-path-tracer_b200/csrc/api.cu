@@ -201,6 +201,8 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
             ptb::g_options.wave_paths = value;
         } else if (n == "count_visits") {
             ptb::g_options.count_visits = value ? 1 : 0;
+        } else if (n == "time_stages") {
+            ptb::g_options.time_stages = value ? 1 : 0;
         } else if (n == "extend_blocks_per_sm") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_blocks_per_sm out of range");
             ptb::g_options.extend_blocks_per_sm = value;

@@ -52,7 +52,16 @@ struct Workspace {
     DeviceBuf path[2][4]; // ping-pong × {ray_o, ray_d, thr, rad}
     DeviceBuf hits, t, sample_out, counters, qcount, accum, claimed, io_a, io_b, io_c;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> stage_ev; // pool for per-launch timing (option time_stages)
     std::mutex lock;
+    cudaEvent_t stage_event(size_t i) {
+        while (stage_ev.size() <= i) {
+            cudaEvent_t e;
+            PTB_CUDA(cudaEventCreate(&e));
+            stage_ev.push_back(e);
+        }
+        return stage_ev[i];
+    }
     void events() {
         for (auto& e : ev)
             if (!e) PTB_CUDA(cudaEventCreate(&e));
@@ -145,20 +154,38 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
     PTB_CUDA(cudaEventRecord(w.ev[0], st));
 
     uint64_t launches = 0, extend_launches = 0, paths = 0;
+    const bool time_stages = g_options.time_stages != 0 && stats != nullptr;
+    size_t n_stage_ev = 0;            // events used: [2k], [2k+1] bracket launch k
+    std::vector<uint8_t> stage_kind;  // 0 extend, 1 shade (+raygen/accumulate)
+    auto stage_begin = [&](uint8_t kind) {
+        if (!time_stages) return;
+        PTB_CUDA(cudaEventRecord(w.stage_event(n_stage_ev++), st));
+        stage_kind.push_back(kind);
+    };
+    auto stage_end = [&]() {
+        if (!time_stages) return;
+        PTB_CUDA(cudaEventRecord(w.stage_event(n_stage_ev++), st));
+    };
     for (uint32_t s0 = 0; s0 < req.spp; s0 += (uint32_t)wave_samples) {
         g.wave_samples = (uint32_t)std::min<uint64_t>(wave_samples, req.spp - s0);
         g.first_sample = req.first_sample + s0;
         paths += uint64_t(req.w) * req.h * g.wave_samples;
         PTB_CUDA(cudaMemsetAsync(qcount, 0, n_counters * 2 * sizeof(uint32_t), st));
+        stage_begin(1);
         launch_raygen(s->d, g, rp, path_set(w, 0), (float4*)w.sample_out.p, &qcount[0], cfg, st);
+        stage_end();
         launches++;
         int cur = 0;
         uint32_t it = 0;
         for (; it < n_iters_fixed; it++) {
             const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
+            stage_begin(0);
             launch_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg, st);
+            stage_end();
+            stage_begin(1);
             launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
                          &qcount[it + 1], counters, cfg, st);
+            stage_end();
             launches += 2;
             extend_launches++;
             cur ^= 1;
@@ -170,16 +197,22 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
                 PTB_CUDA(cudaStreamSynchronize(st));
                 if (live == 0) break;
                 const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
+                stage_begin(0);
                 launch_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg,
                               st);
+                stage_end();
+                stage_begin(1);
                 launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
                              &qcount[it + 1], counters, cfg, st);
+                stage_end();
                 launches += 2;
                 extend_launches++;
                 cur ^= 1;
             }
         }
+        stage_begin(1);
         launch_accumulate(g, (const float4*)w.sample_out.p, rgba_dev, (uint8_t*)w.claimed.p, transparent, st);
+        stage_end();
         launches++;
     }
     PTB_CUDA(cudaEventRecord(w.ev[1], st));
@@ -200,6 +233,11 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
         stats->node_visits = hc.node_visits;
         stats->leaf_visits = hc.leaf_visits;
         stats->tri_tests = hc.tri_tests;
+        for (size_t k = 0; k < stage_kind.size(); k++) {
+            float sms = 0;
+            PTB_CUDA(cudaEventElapsedTime(&sms, w.stage_ev[2 * k], w.stage_ev[2 * k + 1]));
+            (stage_kind[k] == 0 ? stats->extend_seconds : stats->shade_seconds) += sms * 1e-3;
+        }
     }
 }
 

@@ -298,8 +298,10 @@ int ptb_extend_registers(void);
 
 /* ----------------------------------------------------------------- misc -- */
 
-/* Options: "wave_paths" (paths per wavefront), "count_visits" (0/1),
- * "extend_blocks_per_sm", "sort_rays" (0/1). Unknown names → PTB_E_INVALID. */
+/* Options: "wave_paths" (paths per wavefront), "count_visits" (0/1: instrumented
+ * extend kernel), "time_stages" (0/1: CUDA events around every extend / shade
+ * launch, filling extend_seconds / shade_seconds), "extend_blocks_per_sm",
+ * "shade_blocks_per_sm".  Unknown names → PTB_E_INVALID. */
 ptb_status ptb_set_option(const char* name, int64_t value);
 
 const char* ptb_last_error(void);

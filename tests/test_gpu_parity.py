@@ -1,0 +1,227 @@
+"""GPU (B200): the CUDA path through the C ABI against the golden vectors, the plain-C oracle and — where
+oracle/_ref travelled — the reference library itself.  Integer / index results and every float that the
+closest-hit search produces are compared BIT-EXACTLY (the north star only asks for 1e-5 on t and
+barycentrics); images are compared statistically in linear radiance, tolerances stated in each test."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cornell(ptb, procedural):
+    s = ptb.Scene.load_gltf(procedural.cornell_gltf_path(), device=0)
+    yield s
+    s.close()
+
+
+def test_library_is_the_cuda_one(ptb):
+    assert ptb.device_count() >= 1
+    assert ptb.lib().ptb_extend_registers() > 0  # the sm_100a kernel image loaded
+
+
+def test_scene_trees_on_device_match_reference(cornell):
+    kd = H.load("cornell_kd.npz")
+    for m in range(7):
+        assert np.array_equal(cornell.dump_kd(m), kd[f"mesh{m}"])
+    info = cornell.info()
+    assert info["n_triangles"] == 1008 and info["n_instances"] == 5 and info["n_surfaces"] == 7
+
+
+@pytest.mark.parametrize("key", ["cam", "rnd", "bounce"])
+def test_cornell_closest_hits_bit_exact(cornell, key):
+    r = H.load("cornell_rays.npz")
+    hits, attrs = cornell.trace_rays(r[key + "_rays"], attrs=True)
+    H.assert_hits_equal(hits, r[key + "_hits"], "cornell:" + key)
+    # positions / normals / tangents / uv: same operation order, no transcendental → also bit-exact
+    assert np.array_equal(H.bits(attrs), H.bits(r[key + "_attrs"]))
+
+
+def test_camera_rays_bit_exact(cornell):
+    r = H.load("cornell_rays.npz")
+    w, h = (int(x) for x in r["cam_res"])
+    od = cornell.camera_rays(w, h, r["cam_px"], r["cam_py"], r["cam_aa"])
+    assert np.array_equal(H.bits(od), H.bits(r["cam_rays"]))
+
+
+def test_transformed_instances_and_sun_scene(ptb):
+    z = H.load("sun_scene_rays.npz")
+    with ptb.Scene.create(H.make_flat(ptb.SceneDescription, H.scene_parts_from_npz(z))) as s:
+        for key in ("cam", "rnd", "bounce"):
+            hits, attrs = s.trace_rays(z[key + "_rays"], attrs=True)
+            H.assert_hits_equal(hits, z[key + "_hits"], "sun scene:" + key)
+            assert np.array_equal(H.bits(attrs), H.bits(z[key + "_attrs"]))
+
+
+def test_heightfield_golden_and_visit_counts(ptb, procedural):
+    with ptb.Scene.create(procedural.heightfield_scene(40)) as s:
+        kd = H.load("heightfield40_kd.npz")
+        assert np.array_equal(s.dump_kd(0), kd["mesh0"])
+        r = H.load("heightfield40_rays.npz")
+        for key in ("cam", "rnd", "bounce"):
+            H.assert_hits_equal(s.trace_rays(r[key + "_rays"]), r[key + "_hits"], "heightfield40:" + key)
+        # the instrumented kernel counts exactly what the reference algorithm visits
+        ptb.set_option("count_visits", 1)
+        try:
+            _, st = s.trace_rays(r["cam_rays"], stats=True)
+        finally:
+            ptb.set_option("count_visits", 0)
+        _, _, branch, leaf, tri, _ = (int(x) for x in r["visits_cam"])
+        assert (st["node_visits"], st["leaf_visits"], st["tri_tests"]) == (branch, leaf, tri)
+        assert st["rays"] == len(r["cam_rays"])
+
+
+def test_large_mesh_against_c_oracle(ptb, procedural, portlib, reflib):
+    """125 000 triangles, 400 000 seeded rays incl. edge cases: axis-parallel, origin on the surface,
+    far outside, un-normalised, zero-length direction."""
+    desc = procedural.heightfield_scene(250)
+    rng = np.random.default_rng(42)
+    n = 400_000
+    o = (rng.uniform(-6, 6, (n, 3)) * (1, 0.25, 1) + (0, 1.0, 0)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:5000, 0] = 0
+    d[5000:10000, 1] = 0
+    d[10000:12000] = (0, -1, 0)
+    d[12000:14000] *= np.float32(1e-3)
+    o[14000:16000] *= np.float32(40)
+    d[16000:16010] = 0  # degenerate direction: NaN everywhere, must come out as a miss on both sides
+    od = np.concatenate([o, d], 1)
+    with ptb.Scene.create(desc) as s:
+        got = s.trace_rays(od)
+    port = portlib.PortScene(reflib.FlatScene(desc.meshes, desc.surfaces, desc.instances, desc.materials, desc.camera))
+    want = port.trace_rays(od)
+    H.assert_hits_equal(got, want, "heightfield250 vs C oracle")
+    assert (want["instance"][16000:16010] == 0xFFFFFFFF).all()
+
+
+def test_empty_and_tiny_inputs(cornell):
+    assert len(cornell.trace_rays(np.zeros((0, 6), np.float32))) == 0
+    one = cornell.trace_rays(np.array([[0, 2.3, 11.7, 0, 0, -1]], np.float32))
+    assert one["instance"][0] != 0xFFFFFFFF
+
+
+def test_tonemap_matches_reference_encode(ptb):
+    t = H.load("tonemap.npz")
+    got = ptb.tonemap_rgba8(t["rgb"], t["alpha"])
+    diff = np.abs(got.astype(np.int16) - t["rgba8"].astype(np.int16))
+    # powf on the device is not glibc's: the byte may differ by one where v*255+0.5 sits on an integer
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.01
+    assert np.array_equal(got[:, 3], t["rgba8"][:, 3])  # alpha has no pow: exact
+
+
+@pytest.mark.parametrize("name,mode,depth", [("A", 0, 4), ("B", 1, 8)])
+def test_image_statistics_against_converged_reference(cornell, name, mode, depth):
+    """Linear radiance, Cornell 64x64.  Tolerances: per-channel image mean within 4 sigma of the
+    converged reference image (sigma from the reference's own per-pixel sample variance), RMSE against it
+    within [0.6, 1.5] x the value that variance predicts, and the rays-per-path ratio of the reference."""
+    conv = H.load(f"cornell_converged_{name}.npz")
+    assert int(conv["depth"]) == depth
+    spp = 512
+    rgb, alpha, st = cornell.render_tile(64, 64, spp, depth, seed=99, integrator=mode)
+    assert not np.isnan(rgb).any()
+    z = H.mean_z(rgb, conv, spp)
+    assert np.all(np.abs(z) < 4.0), z
+    rmse = np.sqrt(((rgb - conv["mean"]) ** 2).mean())
+    expect = np.sqrt((conv["sigma_per_sample"].astype(np.float64) ** 2).mean() * (1.0 / spp + 1.0 / float(conv["spp"])))
+    assert 0.6 * expect < rmse < 1.5 * expect, (rmse, expect)
+    assert np.all(alpha == 1.0)
+    want_rpp = 3.82 if mode == 0 else 5.03
+    assert abs(st["rays"] / st["paths"] - want_rpp) < 0.05
+    # per-pixel: no pixel further than 6 sigma of its own noise from the converged value
+    se = conv["sigma_per_sample"] * np.sqrt(1.0 / spp + 1.0 / float(conv["spp"])) + 1e-3
+    assert (np.abs(rgb - conv["mean"]) / se).max() < 8.0
+
+
+def test_image_statistics_against_live_reference_sun_scene(ptb, reflib):
+    """Sun light + shadow rays (traced inside shade) against the reference library itself on the GPU box."""
+    if not reflib.available():
+        pytest.skip("oracle/_ref not built")
+    z = H.load("sun_scene_rays.npz")
+    parts = H.scene_parts_from_npz(z)
+    ref = reflib.RefScene.from_flat(H.make_flat(reflib.FlatScene, parts))
+    with ptb.Scene.create(H.make_flat(ptb.SceneDescription, parts)) as s:
+        for mode, ref_mode, depth in ((0, 0, 4), (1, 1, 6)):
+            r_rgb, _, r_rays, _ = ref.render_linear(64, 48, 256, depth, mode=2 if mode == 0 else 1)
+            rgb, _, st = s.render_tile(64, 48, 1024, depth, seed=5, integrator=mode)
+            # both are noisy: compare image means with the pooled standard error estimated from 8x8 blocks
+            def block_means(a):
+                return a.reshape(6, 8, 8, 8, 3).mean((1, 3)).reshape(-1, 3)
+            diff = block_means(rgb) - block_means(r_rgb)
+            se = diff.std(0) / np.sqrt(len(diff)) + 1e-4
+            assert np.all(np.abs(diff.mean(0)) < 5 * se + 0.01 * np.abs(r_rgb.mean((0, 1)))), (diff.mean(0), se)
+            assert abs(st["rays"] / st["paths"] - r_rays / (64 * 48 * 256)) < 0.05
+
+
+def test_render_is_deterministic_and_tiles_compose(cornell):
+    """Size-independent properties: same seed → identical image; a frame rendered as four tiles equals the
+    full-frame render bit for bit (RNG is keyed by global pixel and sample); sample ranges chain."""
+    full, a_full, _ = cornell.render_tile(96, 64, 8, 4, seed=3)
+    again, _, _ = cornell.render_tile(96, 64, 8, 4, seed=3)
+    assert np.array_equal(H.bits(full), H.bits(again))
+    other, _, _ = cornell.render_tile(96, 64, 8, 4, seed=4)
+    assert not np.array_equal(H.bits(full), H.bits(other))
+    tiled = np.zeros_like(full)
+    for (x0, y0, w, h) in ((0, 0, 50, 30), (50, 0, 46, 30), (0, 30, 50, 34), (50, 30, 46, 34)):
+        t, _, _ = cornell.render_tile(96, 64, 8, 4, tile=(x0, y0, w, h), seed=3)
+        tiled[y0:y0 + h, x0:x0 + w] = t
+    assert np.array_equal(H.bits(full), H.bits(tiled))
+
+
+def test_wave_size_does_not_change_the_image(ptb, cornell):
+    """The running mean is folded in sample order whatever the wavefront size."""
+    a, _, _ = cornell.render_tile(64, 64, 16, 4, seed=8)
+    ptb.set_option("wave_paths", 64 * 64 * 3)
+    try:
+        b, _, _ = cornell.render_tile(64, 64, 16, 4, seed=8)
+    finally:
+        ptb.set_option("wave_paths", 8 << 20)
+    assert np.array_equal(H.bits(a), H.bits(b))
+
+
+def test_transparent_background_and_zero_depth(ptb, procedural):
+    d = procedural.heightfield_scene(16)
+    d.transparent_background = True
+    d.camera = (np.array([0, 3, 12], np.float32), d.camera[1], 0.9)  # part of the frame sees the sky
+    with ptb.Scene.create(d) as s:
+        rgb, alpha, st = s.render_tile(64, 36, 16, 4, seed=1)
+        assert set(np.unique(alpha)).issubset({0.0, 1.0}) or ((alpha >= 0) & (alpha <= 1)).all()
+        assert (alpha == 0).any() and (alpha == 1).any()
+        assert np.all(rgb[alpha == 0] == 0)  # unclaimed pixels keep transparent black (renderer.cpp:388-392)
+        rgb0, alpha0, st0 = s.render_tile(64, 36, 4, 0, seed=1)
+        assert st0["rays"] == 0 and np.all(rgb0 == 0) and np.all(alpha0 == 1)  # trace(0) = fvec4::future
+
+
+def test_full_size_c2_properties(ptb, procedural):
+    """BASELINE configs[1] geometry at full size (999 698 triangles): tree statistics of the survey probe,
+    a full 1080p wave, ray accounting, determinism."""
+    desc = procedural.heightfield_scene(707)
+    with ptb.Scene.create(desc) as s:
+        info = s.info()
+        assert info["n_triangles"] == 999_698 + 8
+        assert info["kd_max_depth_reached"] == 25
+        assert 5.5 < info["n_leaf_refs"] / info["n_triangles"] < 7.0  # 6.2x duplication in the survey probe
+        rgb, alpha, st = s.render_tile(1920, 1080, 2, 4, seed=1)
+        assert st["paths"] == 1920 * 1080 * 2
+        assert st["paths"] <= st["rays"] <= 4 * st["paths"]
+        assert np.isfinite(rgb).all() and rgb.min() >= 0
+        rgb2, _, st2 = s.render_tile(1920, 1080, 2, 4, seed=1)
+        assert st2["rays"] == st["rays"] and np.array_equal(H.bits(rgb), H.bits(rgb2))
+        # primary rays: the terrain fills the frame
+        ys, xs = np.mgrid[0:270, 0:480]
+        od = s.camera_rays(480, 270, xs.ravel(), ys.ravel(), np.full((480 * 270, 2), 0.5, np.float32))
+        hits = s.trace_rays(od)
+        assert (hits["instance"] == 0).mean() > 0.99
+
+
+def test_renderer_mirror_and_worker_request(ptb, procedural):
+    r = ptb.Renderer()
+    r.resolution = (48, 48)
+    r.sample_count = 8
+    r.bounce_count = 4
+    r.load_gltf(procedural.cornell_gltf_path())
+    img = r.render()
+    assert img.shape == (48, 48, 4) and img.dtype == np.uint8 and (img[..., 3] == 255).all()
+    rgba, st = ptb.worker_render(r.scene, samples=4, bounces=6, X=40, Y=30)
+    assert rgba.shape == (30, 40, 4) and st["paths"] == 40 * 30 * 4

@@ -1,0 +1,156 @@
+"""CPU: host logic of the product (KD builder, glTF loader, PNG, C-ABI surface) — no compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+def test_abi_exports_every_declared_symbol(ptb):
+    header = open(ptb.HEADER_PATH).read()
+    declared = set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", header))
+    lib = ptb.lib()
+    assert declared, "no declarations found in include/ptb.h"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libptb.so does not export {name}"
+    assert declared == set(ptb.EXPORTS), declared ^ set(ptb.EXPORTS)
+    assert lib.ptb_abi_version() == 1
+
+
+def test_struct_layouts_match_header(ptb):
+    assert ctypes.sizeof(ptb.TileReq) == 56
+    assert ptb.HIT_DTYPE.itemsize == 28
+    assert ctypes.sizeof(ptb.MaterialDesc) == 4 * (3 + 1 + 1 + 1 + 3 + 1 + 1 + 6)
+    assert ctypes.sizeof(ptb.InstanceDesc) == 4 * (3 + 9 + 2)
+
+
+def test_no_gpu_means_error_not_fallback(ptb, procedural):
+    """Without a CUDA device scene creation must FAIL with PTB_E_CUDA (there is no CPU path)."""
+    if ptb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.Scene.create(procedural.heightfield_scene(4))
+    assert e.value.status == ptb.PTB_E_CUDA
+
+
+def test_invalid_descriptions_are_rejected(ptb, procedural):
+    d = procedural.heightfield_scene(4)
+    d.meshes[0]["indices"][0, 0] = 10 ** 6
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.Scene.create(d)
+    assert e.value.status == ptb.PTB_E_INVALID
+    with pytest.raises(ptb.PtbError):
+        ptb.set_option("no_such_option", 1)
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.load_gltf_description("/nonexistent/scene.gltf")
+    assert e.value.status == ptb.PTB_E_IO
+
+
+def test_kd_builder_reproduces_reference_trees_cornell(ptb):
+    z = H.load("cornell_scene.npz")
+    kd = H.load("cornell_kd.npz")
+    for m in range(int(z["n_meshes"])):
+        words, aabb = ptb.host_build_kd(z[f"mesh{m}_positions"], z[f"mesh{m}_indices"])
+        assert np.array_equal(words, kd[f"mesh{m}"]), f"mesh {m}"
+        assert np.array_equal(H.bits(aabb), H.bits(kd["mesh_aabbs"][m]))
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_kd_builder_heightfield_any_thread_count(ptb, procedural, threads):
+    m = procedural.heightfield_mesh(40)
+    words, _ = ptb.host_build_kd(m["positions"], m["indices"], threads=threads)
+    assert np.array_equal(words, H.load("heightfield40_kd.npz")["mesh0"])
+
+
+def test_kd_builder_against_c_oracle_on_awkward_meshes(ptb, portlib, reflib):
+    """Degenerate / axis-aligned / duplicated / all-negative geometry: ties in the SAH sweep, the
+    FLT_MIN quirk of aabb::clear, empty children."""
+    rng = np.random.default_rng(3)
+    cases = []
+    # all-negative coordinates (max of the box starts at FLT_MIN, the smallest positive float)
+    p = -rng.random((60, 3)).astype(np.float32) - 1
+    cases.append((p, rng.integers(0, 60, (80, 3))))
+    # axis-aligned quads stacked on a lattice: many equal event positions, flat triangles
+    g = np.stack(np.meshgrid(np.arange(5), np.arange(5), np.arange(3), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    idx = rng.integers(0, len(g), (150, 3))
+    cases.append((g, idx))
+    # exact duplicates and zero-area triangles
+    p = rng.random((30, 3)).astype(np.float32)
+    idx = np.concatenate([rng.integers(0, 30, (40, 3)), np.array([[1, 1, 1], [2, 2, 5], [7, 8, 9], [7, 8, 9]])])
+    cases.append((p, idx))
+    # single triangle and empty mesh
+    cases.append((p, np.array([[0, 1, 2]])))
+    cases.append((p, np.zeros((0, 3), np.int64)))
+    for pos, idx in cases:
+        idx = np.ascontiguousarray(idx, np.uint32)
+        for use_sah in (True, False):
+            # the median builder splits every node down to the depth limit (2^depth leaves): keep it shallow
+            for depth in ((25, 6) if use_sah else (7,)):
+                words, aabb = ptb.host_build_kd(pos, idx, use_sah=use_sah, max_depth=depth)
+                nv = len(pos)
+                mesh = dict(positions=pos, normals=np.zeros((nv, 3), np.float32), tangents=np.zeros((nv, 3), np.float32),
+                            uvs=np.zeros((nv, 2), np.float32), indices=idx)
+                flat = reflib.FlatScene([mesh], [(0, 0)], [((0, 0, 0), (1, 0, 0, 0, 1, 0, 0, 0, 1), 0, 1)],
+                                        [dict()], ((0, 0, 5), (1, 0, 0, 0, 1, 0, 0, 0, 1), 0.7),
+                                        kd_use_sah=use_sah, kd_max_depth=depth)
+                port = portlib.PortScene(flat)
+                assert np.array_equal(words, port.dump_kd(0)), (len(idx), use_sah, depth)
+                assert np.array_equal(H.bits(aabb), H.bits(port.mesh_aabb(0)))
+
+
+def test_gltf_loader_reproduces_reference_scene(ptb, procedural):
+    """Vertices, scrambled tangents, transforms, materials, camera and the renderer::intersect visiting
+    order, bit for bit against the flat export of the reference's loader."""
+    got = ptb.load_gltf_description(procedural.cornell_gltf_path())
+    z = H.load("cornell_scene.npz")
+    want = H.scene_parts_from_npz(z)
+    assert len(got.meshes) == len(want["meshes"])
+    for a, b in zip(got.meshes, want["meshes"]):
+        for k in H.MESH_KEYS:
+            assert np.array_equal(H.bits(a[k]), H.bits(b[k])), k
+    assert np.array_equal(got.surfaces, want["surfaces"])
+    for a, b in zip(got.instances, want["instances"]):
+        assert np.array_equal(H.bits(a[0]), H.bits(b[0])) and np.array_equal(H.bits(a[1]), H.bits(b[1]))
+        assert a[2:] == b[2:]
+    for a, b in zip(got.materials, want["materials"]):
+        for k in ("albedo", "opacity", "roughness", "metallic", "emissive", "ior"):
+            assert np.array_equal(np.float32(a[k]), np.float32(b[k])), k
+        assert a["albedo_tex"] == ptb.NO_TEXTURE
+    assert np.array_equal(H.bits(got.camera[0]), H.bits(want["camera"][0]))
+    assert np.array_equal(H.bits(got.camera[1]), H.bits(want["camera"][1]))
+    assert np.float32(got.camera[2]) == np.float32(want["camera"][2])
+    assert got.sun is None
+
+
+def test_gltf_loader_errors(ptb, tmp_path):
+    bad = tmp_path / "bad.gltf"
+    bad.write_text("{ not json")
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.load_gltf_description(str(bad))
+    assert e.value.status == ptb.PTB_E_IO
+    nocam = tmp_path / "nocam.gltf"
+    nocam.write_text('{"asset":{"version":"2.0"},"scenes":[{"nodes":[]}],"nodes":[]}')
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.load_gltf_description(str(nocam))
+    assert "camera" in str(e.value)  # renderer.cpp:73-74
+
+
+def test_png_round_trip(ptb, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    path = str(tmp_path / "x.png")
+    ptb.write_png(path, img)
+    assert np.array_equal(np.asarray(Image.open(path)), img)
+
+
+def test_tile_request_validation_needs_no_gpu(ptb):
+    """NULL handles are refused before anything touches CUDA."""
+    req = ptb.TileReq(8, 8, 0, 0, 8, 8, 1, 1, 1, 0, 0, 0, 0)
+    rgb = np.zeros((8, 8, 3), np.float32)
+    st = ptb.lib().ptb_render_tile(None, ctypes.byref(req), rgb.ctypes.data_as(ptb.f32p), None, None)
+    assert st == ptb.PTB_E_INVALID
+    assert b"NULL" in ptb.lib().ptb_last_error()
