@@ -123,7 +123,7 @@ EXPORTS = [
     "ptb_scene_create", "ptb_scene_load_gltf", "ptb_scene_destroy", "ptb_scene_get_info", "ptb_scene_dump_kd",
     "ptb_trace_rays", "ptb_trace_rays_attrs", "ptb_render_tile", "ptb_render_tile_dev", "ptb_tonemap_rgba8",
     "ptb_write_png", "ptb_host_build_kd", "ptb_desc_load_gltf", "ptb_desc_get", "ptb_desc_free",
-    "ptb_camera_rays", "ptb_trace_rays_stats", "ptb_extend_registers", "ptb_set_option", "ptb_last_error",
+    "ptb_camera_rays", "ptb_trace_rays_stats", "ptb_extend_registers", "ptb_selftest_division", "ptb_set_option", "ptb_last_error",
     "ptb_abi_version", "ptb_device_count",
 ]
 
@@ -182,6 +182,8 @@ def lib():
     L.ptb_abi_version.restype = C.c_int
     L.ptb_device_count.restype = C.c_int
     L.ptb_extend_registers.restype = C.c_int
+    L.ptb_selftest_division.restype = C.c_uint64
+    L.ptb_selftest_division.argtypes = [C.c_uint64, C.c_uint64]
     _lib = L
     return L
 

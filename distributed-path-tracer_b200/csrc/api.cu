@@ -201,6 +201,9 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
             ptb::g_options.wave_paths = value;
         } else if (n == "count_visits") {
             ptb::g_options.count_visits = value ? 1 : 0;
+        } else if (n == "extend_variant") {
+            if (value < 0 || value > 1) throw ptb::Error(PTB_E_INVALID, "extend_variant must be 0 or 1");
+            ptb::g_options.extend_variant = value;
         } else if (n == "time_stages") {
             ptb::g_options.time_stages = value ? 1 : 0;
         } else if (n == "extend_blocks_per_sm") {
@@ -222,6 +225,9 @@ int ptb_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
-int ptb_extend_registers(void) { return ptb::extend_regs_per_thread(); }
+int ptb_extend_registers(void) {
+    return ptb::g_options.extend_variant == 0 ? ptb::extend_regs_per_thread() : ptb::extend_lanes_regs_per_thread();
+}
+uint64_t ptb_selftest_division(uint64_t n, uint64_t seed) { return ptb::division_selftest(n, seed); }
 
 } // extern "C"

@@ -47,6 +47,7 @@ struct LaunchCfg {
     int extend_blocks_per_sm;
     int shade_blocks_per_sm;
     bool count_visits;
+    int extend_variant; // 0: one thread per ray (kernels.cu), 1: lane state machine (extend.cu)
 };
 
 // qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.
@@ -69,6 +70,13 @@ void launch_export_hits(const DScene& S, const uint4* hits, const float* t, uint
                         float* attrs_out /*14 per ray or null*/, cudaStream_t st);
 void launch_camera_rays(const DScene& S, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py,
                         const float* aa, uint64_t n, float* origin_dir, cudaStream_t st);
+
+// extend.cu — the lane-state-machine closest-hit kernel (default); launch_extend is the first, simple kernel
+void launch_extend_lanes(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
+                         const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
+                         cudaStream_t st);
+int extend_lanes_regs_per_thread();
+unsigned long long division_selftest(uint64_t n, uint64_t seed);
 
 int extend_regs_per_thread();
 

@@ -82,12 +82,21 @@ PathBuffers path_set(Workspace& w, int i) {
                        (float4*)w.path[i][3].p};
 }
 
+void run_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
+                const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg, cudaStream_t st) {
+    if (cfg.extend_variant == 0)
+        launch_extend(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
+    else
+        launch_extend_lanes(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
+}
+
 LaunchCfg launch_cfg(const ptb_scene* s) {
     LaunchCfg c;
     c.sm_count = s->sm_count;
     c.extend_blocks_per_sm = (int)g_options.extend_blocks_per_sm;
     c.shade_blocks_per_sm = (int)g_options.shade_blocks_per_sm;
     c.count_visits = g_options.count_visits != 0;
+    c.extend_variant = (int)g_options.extend_variant;
     return c;
 }
 
@@ -180,7 +189,7 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
         for (; it < n_iters_fixed; it++) {
             const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
             stage_begin(0);
-            launch_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg, st);
+            run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg, st);
             stage_end();
             stage_begin(1);
             launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
@@ -198,7 +207,7 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
                 if (live == 0) break;
                 const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
                 stage_begin(0);
-                launch_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg,
+                run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg,
                               st);
                 stage_end();
                 stage_begin(1);
@@ -289,7 +298,7 @@ void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, pt
     PTB_CUDA(cudaMemcpyAsync(w.io_a.p, origin_dir, n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
     launch_prep_rays((const float*)w.io_a.p, n, (float4*)w.path[0][0].p, (float4*)w.path[0][1].p, st);
     PTB_CUDA(cudaEventRecord(w.ev[0], st));
-    launch_extend(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint4*)w.hits.p, (float*)w.t.p,
+    run_extend(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint4*)w.hits.p, (float*)w.t.p,
                   &qc[0], &qc[1], (DeviceCounters*)w.counters.p, launch_cfg(s), st);
     PTB_CUDA(cudaEventRecord(w.ev[1], st));
     launch_export_hits(s->d, (const uint4*)w.hits.p, (const float*)w.t.p, n, w.io_b.p,

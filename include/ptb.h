@@ -296,12 +296,21 @@ ptb_status ptb_trace_rays_stats(const ptb_scene* scene, const float* origin_dir,
 /* Registers per thread of the extend kernel as loaded (cudaFuncGetAttributes). */
 int ptb_extend_registers(void);
 
+/* The extend kernel computes the split-plane distance (split - o) / d
+ * (LIB/core/mesh.cpp:336-337) through a per-ray reciprocal and three FMAs, the
+ * fast path of an IEEE division.  This runs n random operand pairs inside the
+ * guarded exponent window through that shortcut on the GPU and returns how many
+ * differ from the correctly rounded quotient (must be 0; ~0ull on a CUDA error). */
+uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
+
 /* ----------------------------------------------------------------- misc -- */
 
 /* Options: "wave_paths" (paths per wavefront), "count_visits" (0/1: instrumented
  * extend kernel), "time_stages" (0/1: CUDA events around every extend / shade
- * launch, filling extend_seconds / shade_seconds), "extend_blocks_per_sm",
- * "shade_blocks_per_sm".  Unknown names → PTB_E_INVALID. */
+ * launch, filling extend_seconds / shade_seconds), "extend_variant" (1: lane
+ * state machine with ray replacement, default; 0: the first one-thread-per-ray
+ * kernel, kept for A/B checks), "extend_blocks_per_sm", "shade_blocks_per_sm".
+ * Unknown names → PTB_E_INVALID. */
 ptb_status ptb_set_option(const char* name, int64_t value);
 
 const char* ptb_last_error(void);

@@ -22,6 +22,25 @@ def test_library_is_the_cuda_one(ptb):
     assert ptb.lib().ptb_extend_registers() > 0  # the sm_100a kernel image loaded
 
 
+def test_division_shortcut_is_exact(ptb):
+    """The extend kernel's (split - o) / d through a refined reciprocal + 3 FMAs must be the IEEE quotient."""
+    assert ptb.lib().ptb_selftest_division(1 << 30, 12345) == 0
+    assert ptb.lib().ptb_selftest_division(1 << 28, 777) == 0
+
+
+@pytest.fixture(params=[1, 0], ids=["lanes", "simple"])
+def extend_variant(ptb, request):
+    ptb.set_option("extend_variant", request.param)
+    yield request.param
+    ptb.set_option("extend_variant", 1)
+
+
+def test_both_extend_kernels_against_goldens(cornell, extend_variant):
+    r = H.load("cornell_rays.npz")
+    for key in ("cam", "rnd", "bounce"):
+        H.assert_hits_equal(cornell.trace_rays(r[key + "_rays"]), r[key + "_hits"], f"variant {extend_variant}:{key}")
+
+
 def test_scene_trees_on_device_match_reference(cornell):
     kd = H.load("cornell_kd.npz")
     for m in range(7):
