@@ -11,7 +11,7 @@
 //   meshes[]     per unique mesh: AABB + offsets into the arrays below
 //   kd_nodes[]   8-byte nodes, all meshes back to back (kd_build.hpp)
 //   kd_refs[]    leaf → triangle references (u32, index into tri_* of the mesh)
-//   tri_a/ab/ac  float4 per unique triangle: a, a-b, a-c.  The two edge
+//   tri[]        three float4 per unique triangle (one 48-byte record): a, a-b, a-c.  The two edge
 //                differences are what triangle::intersect forms first
 //                (LIB/geometry/triangle.cpp:136-140); they are single float
 //                subtractions, so precomputing them changes no bit.
@@ -90,9 +90,7 @@ struct DScene {
     const DMesh* meshes;
     const uint2* kd_nodes;
     const uint32_t* kd_refs;
-    const float4* tri_a;
-    const float4* tri_ab;
-    const float4* tri_ac;
+    const float4* tri; // 3 float4 per triangle: a, a-b, a-c (.w = the three vertex indices)
     const float* vtx_pos; // 3 per vertex
     const float* vtx_nrm; // 3 per vertex
     const float* vtx_tan; // 3 per vertex

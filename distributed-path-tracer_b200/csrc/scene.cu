@@ -159,7 +159,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
         std::vector<DMesh> meshes(desc.n_meshes);
         std::vector<uint2> nodes;
         std::vector<uint32_t> refs;
-        std::vector<float4> tri_a, tri_ab, tri_ac;
+        std::vector<float4> tri;
         std::vector<float> vpos, vnrm, vtan, vuv;
         s->trees.resize(desc.n_meshes);
         for (uint32_t m = 0; m < desc.n_meshes; m++) {
@@ -169,7 +169,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
             build_kd_tree(md.positions, md.indices, md.n_triangles, box, desc.kd_use_sah != 0, max_depth, 0, tree);
             require(nodes.size() + tree.nodes.size() < (1ull << 32), "KD nodes exceed 32-bit indexing");
             require(refs.size() + tree.refs.size() < (1ull << 32), "KD leaf references exceed 32-bit indexing");
-            require(tri_a.size() + md.n_triangles < (1ull << 32), "triangles exceed 32-bit indexing");
+            require(tri.size() / 3 + md.n_triangles < (1ull << 30), "triangles exceed 30-bit indexing");
             DMesh& dm = meshes[m];
             for (int a = 0; a < 3; a++) {
                 dm.aabb_min[a] = box.min[a];
@@ -177,7 +177,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
             }
             dm.node_base = static_cast<uint32_t>(nodes.size());
             dm.ref_base = static_cast<uint32_t>(refs.size());
-            dm.tri_base = static_cast<uint32_t>(tri_a.size());
+            dm.tri_base = static_cast<uint32_t>(tri.size() / 3);
             dm.vtx_base = static_cast<uint32_t>(vpos.size() / 3);
             dm.n_triangles = md.n_triangles;
             dm.pad = 0;
@@ -193,9 +193,9 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
                 std::memcpy(&w0, &i0, 4);
                 std::memcpy(&w1, &i1, 4);
                 std::memcpy(&w2, &i2, 4);
-                tri_a.push_back(make_float4(a.x, a.y, a.z, w0));
-                tri_ab.push_back(make_float4(ab.x, ab.y, ab.z, w1));
-                tri_ac.push_back(make_float4(ac.x, ac.y, ac.z, w2));
+                tri.push_back(make_float4(a.x, a.y, a.z, w0));
+                tri.push_back(make_float4(ab.x, ab.y, ab.z, w1));
+                tri.push_back(make_float4(ac.x, ac.y, ac.z, w2));
             }
             vpos.insert(vpos.end(), md.positions, md.positions + size_t(md.n_vertices) * 3);
             vnrm.insert(vnrm.end(), md.normals, md.normals + size_t(md.n_vertices) * 3);
@@ -285,9 +285,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
         d.meshes = upload(s, meshes);
         d.kd_nodes = upload(s, nodes);
         d.kd_refs = upload(s, refs);
-        d.tri_a = upload(s, tri_a);
-        d.tri_ab = upload(s, tri_ab);
-        d.tri_ac = upload(s, tri_ac);
+        d.tri = upload(s, tri);
         d.vtx_pos = upload(s, vpos);
         d.vtx_nrm = upload(s, vnrm);
         d.vtx_tan = upload(s, vtan);

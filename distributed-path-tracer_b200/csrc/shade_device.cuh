@@ -88,9 +88,9 @@ __device__ __forceinline__ HitAttrs hit_attributes(const DScene& S, uint32_t ins
     const DMesh& M = S.meshes[sf.mesh];
     const float alpha = 1 - beta - gamma; // triangle.cpp:185
     const uint32_t t = M.tri_base + tri;
-    const uint32_t i0 = M.vtx_base + __float_as_uint(__ldg(&S.tri_a[t].w));
-    const uint32_t i1 = M.vtx_base + __float_as_uint(__ldg(&S.tri_ab[t].w));
-    const uint32_t i2 = M.vtx_base + __float_as_uint(__ldg(&S.tri_ac[t].w));
+    const uint32_t i0 = M.vtx_base + __float_as_uint(__ldg(&S.tri[size_t(t) * 3].w));
+    const uint32_t i1 = M.vtx_base + __float_as_uint(__ldg(&S.tri[size_t(t) * 3 + 1].w));
+    const uint32_t i2 = M.vtx_base + __float_as_uint(__ldg(&S.tri[size_t(t) * 3 + 2].w));
     HitAttrs h;
     h.material = sf.material;
     h.position = apply(I.fwd, ld3(S.vtx_pos, i0) * alpha + ld3(S.vtx_pos, i1) * beta + ld3(S.vtx_pos, i2) * gamma);

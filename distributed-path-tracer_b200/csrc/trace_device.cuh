@@ -151,9 +151,8 @@ __device__ __forceinline__ MeshHit mesh_closest(const DScene& S, const DMesh& M,
             MeshHit best = none;
             for (uint32_t i = 0; i < count; i++) {
                 const uint32_t tri = __ldg(r + i);
-                const float4 a = __ldg(S.tri_a + M.tri_base + tri);
-                const float4 ab = __ldg(S.tri_ab + M.tri_base + tri);
-                const float4 ac = __ldg(S.tri_ac + M.tri_base + tri);
+                const float4* t3 = S.tri + size_t(M.tri_base + tri) * 3;
+                const float4 a = __ldg(t3), ab = __ldg(t3 + 1), ac = __ldg(t3 + 2);
                 if (COUNT) cnt.tri_tests++;
                 float beta, gamma;
                 float dist = tri_test(V3{a.x, a.y, a.z}, V3{ab.x, ab.y, ab.z}, V3{ac.x, ac.y, ac.z}, o, d, beta, gamma);
