@@ -48,6 +48,7 @@ struct LaunchCfg {
     int shade_blocks_per_sm;
     bool count_visits;
     int extend_variant; // 0: one thread per ray (kernels.cu), 1: lane state machine (extend.cu)
+    int extend_steps, extend_tests; // node steps / triangle tests offered per main-loop iteration (variant 1)
 };
 
 // qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.

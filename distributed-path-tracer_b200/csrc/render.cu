@@ -97,6 +97,8 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.shade_blocks_per_sm = (int)g_options.shade_blocks_per_sm;
     c.count_visits = g_options.count_visits != 0;
     c.extend_variant = (int)g_options.extend_variant;
+    c.extend_steps = (int)g_options.extend_steps;
+    c.extend_tests = (int)g_options.extend_tests;
     return c;
 }
 
