@@ -227,16 +227,22 @@ def run_ptb(args):
     cols, rows = cluster.tile_grid_for(world, args.tiles_per_gpu)
     tiles = cluster.make_tiles(full_w, full_h, cols, rows)
     frame = torch.zeros((full_h, full_w, 4), dtype=torch.float32, device=dev)
-    tile_buf = torch.zeros(max(t[2] * t[3] for t in tiles) * 4, dtype=torch.float32, device=dev)
+    n_workers = max(1, args.streams)
+    main_stream = torch.cuda.current_stream()
+    streams = [main_stream] + [torch.cuda.Stream(device=dev) for _ in range(n_workers - 1)]
+    max_px = max(t[2] * t[3] for t in tiles)
+    tile_bufs = [torch.zeros(max_px * 4, dtype=torch.float32, device=dev) for _ in range(n_workers)]
     pinned = torch.empty((full_h, full_w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
-    stream = torch.cuda.current_stream()
+    stream = main_stream
 
-    def render_tile(tile, out_frame, seed, stats=True):
+    def render_tile(tile, out_frame, seed, worker=0, stats=True):
         x0, y0, w, h = tile
-        st = scene.render_tile_dev(tile_buf.data_ptr(), full_w, full_h, spp, depth, tile=tile, seed=seed,
-                                   integrator=integ, stream=stream.cuda_stream, want_stats=stats)
-        out_frame[y0:y0 + h, x0:x0 + w, :] = tile_buf[: w * h * 4].view(h, w, 4)
+        torch.cuda.set_device(dev)  # worker threads start without a current device
+        with torch.cuda.stream(streams[worker]):
+            st = scene.render_tile_dev(tile_bufs[worker].data_ptr(), full_w, full_h, spp, depth, tile=tile, seed=seed,
+                                       integrator=integ, stream=streams[worker].cuda_stream, want_stats=stats)
+            out_frame[y0:y0 + h, x0:x0 + w, :] = tile_bufs[worker][: w * h * 4].view(h, w, 4)
         return st
 
     epoch = [0]
@@ -244,8 +250,15 @@ def run_ptb(args):
     def step(seed, gather):
         frame.zero_()
         epoch[0] += 1
-        return cluster.render_frame(full_w, full_h, tiles, lambda t, f: render_tile(t, f, seed), frame,
-                                    epoch=epoch[0], gather=gather)
+        for s_ in streams[1:]:
+            s_.wait_stream(main_stream)  # tiles start after whatever precedes the step on the main stream
+        r = cluster.render_frame(full_w, full_h, tiles, lambda t, f, wk: render_tile(t, f, seed, wk), frame,
+                                 epoch=epoch[0], gather=False, local_workers=n_workers)
+        for s_ in streams[1:]:
+            main_stream.wait_stream(s_)  # the step ends on the main stream (that is where the events are)
+        if gather and world > 1:
+            dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
+        return r
 
     def barrier():
         if world > 1:
@@ -301,10 +314,10 @@ def run_ptb(args):
     roofline = None
     if rank == 0:
         ptb.set_option("time_stages", 1)
-        st_t = [render_tile(t, frame, 1, stats=True) for t in tiles[:: world]]
+        st_t = [render_tile(t, frame, 1, 0, stats=True) for t in tiles[:: world]]
         ptb.set_option("time_stages", 0)
         ptb.set_option("count_visits", 1)
-        st_c = [render_tile(t, frame, 1, stats=True) for t in tiles[:: world]]
+        st_c = [render_tile(t, frame, 1, 0, stats=True) for t in tiles[:: world]]
         ptb.set_option("count_visits", 0)
         ext_s = sum(s["extend_seconds"] for s in st_t)
         shade_s = sum(s["shade_seconds"] for s in st_t)
@@ -343,7 +356,7 @@ def run_ptb(args):
             "config": {"workload": desc_name + (f", {spp} spp total ({spp0}/GPU)" if world > 1 else ""),
                        "triangles": int(info["n_triangles"]), "kd_nodes": int(info["n_kd_nodes"]),
                        "kd_leaf_refs": int(info["n_leaf_refs"]), "scene_bytes": int(info["device_bytes"]),
-                       "kd_build_s": info["build_seconds"], "tiles": f"{cols}x{rows} work-stolen",
+                       "kd_build_s": info["build_seconds"], "tiles": f"{cols}x{rows} work-stolen, {n_workers} in flight per GPU",
                        "parallelism": f"tiles x{world}", "wave_paths": args.wave_paths,
                        "frames_per_s_1080p64": frames_per_s if args.config == "c2" else None,
                        "rays_per_path": rays_all / max(paths_all, 1),
@@ -382,6 +395,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
     ap.add_argument("--tiles-per-gpu", type=int, default=8)
     ap.add_argument("--wave-paths", type=int, default=8 << 20)
+    ap.add_argument("--streams", type=int, default=2, help="tiles in flight per GPU (host threads / CUDA streams)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

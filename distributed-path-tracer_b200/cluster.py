@@ -16,6 +16,7 @@ test-suite drive the scheduling / merge logic with world_size 2 on gloo and a fa
 """
 from __future__ import annotations
 
+import threading
 import time
 from typing import Callable, List, Sequence, Tuple
 
@@ -56,14 +57,16 @@ class TileCounter:
         self.key = key
         self.store = group_store
         self.local = 0
+        self._lock = threading.Lock()
 
     def next(self) -> int:
-        """Index of the next unclaimed tile, or -1 when the frame is exhausted."""
-        if self.store is None:
-            i = self.local
-            self.local += 1
-        else:
-            i = self.store.add(self.key, 1) - 1
+        """Index of the next unclaimed tile, or -1 when the frame is exhausted (thread-safe)."""
+        with self._lock:
+            if self.store is None:
+                i = self.local
+                self.local += 1
+            else:
+                i = self.store.add(self.key, 1) - 1
         return i if i < self.n else -1
 
 
@@ -81,14 +84,16 @@ def _default_store():
 
 
 def render_frame(full_w: int, full_h: int, tiles: Sequence[Tile],
-                 render_tile_fn: Callable[[Tile, "object"], dict | None], frame, *, epoch: int = 0,
-                 static_assignment: bool = False, gather: bool = True):
+                 render_tile_fn: Callable[[Tile, "object", int], dict | None], frame, *, epoch: int = 0,
+                 static_assignment: bool = False, gather: bool = True, local_workers: int = 1):
     """Renders the tiles this rank claims into ``frame`` and gathers the full frame on rank 0.
 
     frame: a zero-initialised torch tensor [full_h, full_w, C] (device memory under NCCL, CPU under gloo);
            tiles this rank did not render stay zero.
-    render_tile_fn(tile, frame) renders one tile into frame[y0:y0+h, x0:x0+w] and may return a stats dict
-           (its "rays" and "paths" entries are summed).
+    render_tile_fn(tile, frame, worker) renders one tile into frame[y0:y0+h, x0:x0+w] and may return a stats
+           dict (its "rays" and "paths" entries are summed).  ``worker`` in [0, local_workers) identifies the
+           host thread / CUDA stream: with local_workers > 1 several tiles of this rank are in flight at once
+           (each on its own stream), which hides the tail of one tile's kernels behind the next tile's.
     epoch: distinguishes successive frames in the store (a new counter key per frame).
     Returns dict(rays, paths, tiles=[indices this rank rendered], seconds_render, seconds_gather).
     """
@@ -96,33 +101,50 @@ def render_frame(full_w: int, full_h: int, tiles: Sequence[Tile],
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
     store = _default_store() if (dist and not static_assignment) else None
+    stealing = not (static_assignment or (dist and store is None))
     counter = TileCounter(len(tiles), key=f"ptb_tiles_{epoch}", group_store=store)
-    done, rays, paths = [], 0, 0
+    mine = list(range(rank, len(tiles), world))  # round-robin when there is no stealing
+    mine_pos = TileCounter(len(mine))
+    done, totals, errors = [], {"rays": 0, "paths": 0}, []
+    lock = threading.Lock()
+
+    def work(worker: int):
+        try:
+            while True:
+                if stealing:
+                    i = counter.next()
+                else:
+                    j = mine_pos.next()
+                    i = mine[j] if j >= 0 else -1
+                if i < 0:
+                    break
+                st = render_tile_fn(tiles[i], frame, worker)
+                with lock:
+                    done.append(i)
+                    if st:
+                        totals["rays"] += int(st.get("rays", 0))
+                        totals["paths"] += int(st.get("paths", 0))
+        except BaseException as e:  # surfaced on the calling thread
+            errors.append(e)
+
     t0 = time.perf_counter()
-    if static_assignment or (dist and store is None):
-        mine = range(rank, len(tiles), world)  # round-robin fallback: no stealing
-        for i in mine:
-            st = render_tile_fn(tiles[i], frame)
-            done.append(i)
-            if st:
-                rays += int(st.get("rays", 0))
-                paths += int(st.get("paths", 0))
+    if local_workers <= 1:
+        work(0)
     else:
-        while True:
-            i = counter.next()
-            if i < 0:
-                break
-            st = render_tile_fn(tiles[i], frame)
-            done.append(i)
-            if st:
-                rays += int(st.get("rays", 0))
-                paths += int(st.get("paths", 0))
+        threads = [threading.Thread(target=work, args=(w,)) for w in range(local_workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
     t1 = time.perf_counter()
     if dist and gather and world > 1:
         # disjoint tiles + zero elsewhere: SUM onto rank 0 is the gather of the framebuffer
         dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
     t2 = time.perf_counter()
-    return dict(rays=rays, paths=paths, tiles=done, seconds_render=t1 - t0, seconds_gather=t2 - t1)
+    return dict(rays=totals["rays"], paths=totals["paths"], tiles=sorted(done), seconds_render=t1 - t0,
+                seconds_gather=t2 - t1)
 
 
 def all_sum(values: Sequence[float], device=None) -> List[float]:

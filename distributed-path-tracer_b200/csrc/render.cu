@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -68,13 +69,15 @@ struct Workspace {
     }
 };
 
-Workspace& workspace(int device) {
+// One workspace per (device, stream): calls on different streams (e.g. two host threads rendering
+// different tiles) run concurrently on the GPU, each with its own path buffers.
+Workspace& workspace(int device, cudaStream_t stream = nullptr) {
     static std::mutex m;
-    static std::vector<Workspace*> ws;
+    static std::map<std::pair<int, cudaStream_t>, Workspace*> ws;
     std::lock_guard<std::mutex> g(m);
-    if ((int)ws.size() <= device) ws.resize(device + 1, nullptr);
-    if (!ws[device]) ws[device] = new Workspace;
-    return *ws[device];
+    Workspace*& w = ws[{device, stream}];
+    if (!w) w = new Workspace;
+    return *w;
 }
 
 PathBuffers path_set(Workspace& w, int i) {
@@ -113,7 +116,7 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
     if (req.max_depth > 255) throw Error(PTB_E_INVALID, "max_depth above 255 (the reference's bounce_count is uint8_t)");
     if (req.integrator > 1) throw Error(PTB_E_INVALID, "unknown integrator");
     PTB_CUDA(cudaSetDevice(s->device));
-    Workspace& w = workspace(s->device);
+    Workspace& w = workspace(s->device, st);
     std::lock_guard<std::mutex> guard(w.lock);
     w.events();
 

@@ -30,7 +30,7 @@ def _worker(rank, world, port, static, out_dir):
     tiles = cluster.make_tiles(W, H, *cluster.tile_grid_for(world, 4))
     frame = torch.zeros((H, W, 4), dtype=torch.float32)
 
-    def fake_render(tile, out):
+    def fake_render(tile, out, worker):
         x0, y0, w, h = tile
         ys, xs = np.mgrid[y0:y0 + h, x0:x0 + w]
         val = np.stack([xs, ys, xs * 1000 + ys, np.ones_like(xs)], -1).astype(np.float32)
@@ -39,7 +39,8 @@ def _worker(rank, world, port, static, out_dir):
 
     for epoch in range(3):
         frame.zero_()
-        r = cluster.render_frame(W, H, tiles, fake_render, frame, epoch=epoch, static_assignment=static)
+        r = cluster.render_frame(W, H, tiles, fake_render, frame, epoch=epoch, static_assignment=static,
+                                 local_workers=1 + epoch % 2)
         rays, paths = cluster.all_sum([r["rays"], r["paths"]])
         n_tiles = cluster.all_sum([len(r["tiles"])])[0]
         assert (rays, paths, n_tiles) == (W * H * 3, W * H, len(tiles))
