@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
     ap.add_argument("--tiles-per-gpu", type=int, default=8)
     ap.add_argument("--wave-paths", type=int, default=8 << 20)
-    ap.add_argument("--streams", type=int, default=2, help="tiles in flight per GPU (host threads / CUDA streams)")
+    ap.add_argument("--streams", type=int, default=4, help="tiles in flight per GPU (host threads / CUDA streams)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

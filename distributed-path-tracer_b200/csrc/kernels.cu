@@ -92,15 +92,15 @@ __global__ void __launch_bounds__(256)
             aay = u01(r.y);
         }
         const Ray ray = camera_ray(S.camera, gx, gy, aax, aay, g.full_w, g.full_h);
-        out.ray_o[k] = make_float4(ray.o.x, ray.o.y, ray.o.z, __uint_as_float(p));
-        out.ray_d[k] =
-            make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float((rp.max_depth & F_BOUNCE_MASK) | F_PRIMARY));
-        out.thr[k] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        __stcs(out.ray_o + k, make_float4(ray.o.x, ray.o.y, ray.o.z, __uint_as_float(p)));
+        __stcs(out.ray_d + k,
+               make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float((rp.max_depth & F_BOUNCE_MASK) | F_PRIMARY)));
+        __stcs(out.thr + k, make_float4(1.0f, 1.0f, 1.0f, 0.0f));
         // worker::trace_iter starts alpha at the background value (worker.cpp:299); renderer::trace has no such state
         const float alpha0 = (rp.integrator == 1 && S.transparent_background) ? 0.0f : 1.0f;
-        out.rad[k] = make_float4(0.0f, 0.0f, 0.0f, alpha0);
+        __stcs(out.rad + k, make_float4(0.0f, 0.0f, 0.0f, alpha0));
         // bounce_count == 0: trace returns fvec4::future, trace_iter returns (0, alpha0)
-        sample_out[p] = make_float4(0.0f, 0.0f, 0.0f, alpha0);
+        __stcs(sample_out + p, make_float4(0.0f, 0.0f, 0.0f, alpha0));
     }
 }
 
@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(SHADE_THREADS)
         bool alive = false;
         PathState st;
         if (k < n) {
-            const float4 o4 = in.ray_o[k], d4 = in.ray_d[k], t4 = in.thr[k], r4 = in.rad[k];
+            const float4 o4 = __ldcs(in.ray_o + k), d4 = __ldcs(in.ray_d + k), t4 = __ldcs(in.thr + k),
+                         r4 = __ldcs(in.rad + k);
             st.o = V3{o4.x, o4.y, o4.z};
             st.d = V3{d4.x, d4.y, d4.z};
             st.thr = V3{t4.x, t4.y, t4.z};
@@ -339,8 +340,8 @@ __global__ void __launch_bounds__(SHADE_THREADS)
             st.p = __float_as_uint(o4.w);
             st.flags = __float_as_uint(d4.w);
             float4 result;
-            alive = shade_path<APP_RR, HAS_SUN>(S, g, rp, st, hits[k], stack, cnt, result);
-            if (!alive) sample_out[st.p] = result;
+            alive = shade_path<APP_RR, HAS_SUN>(S, g, rp, st, __ldcs(hits + k), stack, cnt, result);
+            if (!alive) __stcs(sample_out + st.p, result);
         }
         const unsigned mask = __ballot_sync(0xFFFFFFFFu, alive);
         uint32_t base = 0;
@@ -348,10 +349,10 @@ __global__ void __launch_bounds__(SHADE_THREADS)
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (alive) {
             const uint32_t k2 = base + __popc(mask & ((1u << lane) - 1u));
-            out.ray_o[k2] = make_float4(st.o.x, st.o.y, st.o.z, __uint_as_float(st.p));
-            out.ray_d[k2] = make_float4(st.d.x, st.d.y, st.d.z, __uint_as_float(st.flags));
-            out.thr[k2] = make_float4(st.thr.x, st.thr.y, st.thr.z, 0.0f);
-            out.rad[k2] = make_float4(st.rad.x, st.rad.y, st.rad.z, st.alpha);
+            __stcs(out.ray_o + k2, make_float4(st.o.x, st.o.y, st.o.z, __uint_as_float(st.p)));
+            __stcs(out.ray_d + k2, make_float4(st.d.x, st.d.y, st.d.z, __uint_as_float(st.flags)));
+            __stcs(out.thr + k2, make_float4(st.thr.x, st.thr.y, st.thr.z, 0.0f));
+            __stcs(out.rad + k2, make_float4(st.rad.x, st.rad.y, st.rad.z, st.alpha));
         }
     }
     if (HAS_SUN) {
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256)
         float4 px = accum[i];
         bool cl = transparent ? (claimed[i] != 0) : false;
         for (uint32_t s = 0; s < g.wave_samples; s++) {
-            const float4 d = sample_out[size_t(s) * g.padded_pixels + q];
+            const float4 d = __ldcs(sample_out + size_t(s) * g.padded_pixels + q);
             const uint32_t sample = g.first_sample + s;
             if (transparent) {
                 if (d.w > 0.5 && !cl) {
