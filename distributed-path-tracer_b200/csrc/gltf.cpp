@@ -435,6 +435,44 @@ void load_gltf(const std::string& path, uint32_t camera_index, uint32_t sun_ligh
             out.instances.push_back(inst);
         }
 
+        // Renumber meshes, materials and textures by first use in visiting order (materials were created in
+        // node-processing order so that the texture cache sees the reference's load order); objects that no
+        // visited surface uses (an overwritten duplicate root entity, the occlusion texture) are dropped.
+        {
+            const uint32_t none = PTB_NO_TEXTURE;
+            std::vector<uint32_t> mesh_map(out.meshes.size(), none), mat_map(out.materials.size(), none),
+                tex_map(out.textures.size(), none);
+            std::vector<OwnedMesh> meshes2;
+            std::vector<ptb_material_desc> mats2;
+            std::vector<OwnedTexture> tex2;
+            for (ptb_surface_desc& sd : out.surfaces) {
+                if (mesh_map[sd.mesh] == none) {
+                    mesh_map[sd.mesh] = static_cast<uint32_t>(meshes2.size());
+                    meshes2.push_back(std::move(out.meshes[sd.mesh]));
+                }
+                if (mat_map[sd.material] == none) {
+                    mat_map[sd.material] = static_cast<uint32_t>(mats2.size());
+                    ptb_material_desc m = out.materials[sd.material];
+                    uint32_t* slots[6] = {&m.normal_tex, &m.albedo_tex, &m.opacity_tex,
+                                          &m.roughness_tex, &m.metallic_tex, &m.emissive_tex};
+                    for (uint32_t* slot : slots) {
+                        if (*slot == none) continue;
+                        if (tex_map[*slot] == none) {
+                            tex_map[*slot] = static_cast<uint32_t>(tex2.size());
+                            tex2.push_back(out.textures[*slot]); // copy: a texture may be shared
+                        }
+                        *slot = tex_map[*slot];
+                    }
+                    mats2.push_back(m);
+                }
+                sd.mesh = mesh_map[sd.mesh];
+                sd.material = mat_map[sd.material];
+            }
+            out.meshes = std::move(meshes2);
+            out.materials = std::move(mats2);
+            out.textures = std::move(tex2);
+        }
+
         // ---- camera, sun ----
         {
             const Xform cx = global(camera_entity);

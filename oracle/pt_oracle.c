@@ -123,6 +123,8 @@ typedef struct po_scene {
     ptb_surface_desc* surfaces;
     po_instance* instances;
     ptb_material_desc* materials;
+    uint32_t n_textures;
+    ptb_texture_desc* textures; /* pixels are owned copies */
     xform camera;
     float tan_half_fov;
     int sun_enabled;
@@ -407,6 +409,12 @@ po_scene* po_scene_create(const ptb_scene_desc* d) {
     }
     s->surfaces = (ptb_surface_desc*)dup_mem(d->surfaces, sizeof(ptb_surface_desc) * d->n_surfaces);
     s->materials = (ptb_material_desc*)dup_mem(d->materials, sizeof(ptb_material_desc) * d->n_materials);
+    s->n_textures = d->n_textures;
+    s->textures = (ptb_texture_desc*)dup_mem(d->textures, sizeof(ptb_texture_desc) * d->n_textures);
+    for (uint32_t t = 0; t < d->n_textures; t++) {
+        const ptb_texture_desc* td = &d->textures[t];
+        s->textures[t].pixels = dup_mem(td->pixels, (size_t)td->width * td->height * td->channels * (td->is_float ? 4 : 1));
+    }
     s->instances = (po_instance*)calloc(d->n_instances ? d->n_instances : 1, sizeof(po_instance));
     for (uint32_t i = 0; i < d->n_instances; i++) {
         const ptb_instance_desc* id = &d->instances[i];
@@ -447,6 +455,8 @@ void po_scene_free(po_scene* s) {
         free((void*)m->indices);
         free_node(m->root);
     }
+    for (uint32_t t = 0; t < s->n_textures; t++) free((void*)s->textures[t].pixels);
+    free(s->textures);
     free(s->meshes); free(s->surfaces); free(s->materials); free(s->instances);
     free(s);
 }
@@ -624,12 +634,60 @@ static attrs_t hit_attrs(const po_scene* s, const scene_hit* h) {
     return a;
 }
 
-/* intersect_result::get_normal with material::get_normal == (0,0,1) (no textures in the port),
- * LIB/core/renderer.cpp:430-435, LIB/core/material.cpp:6-11 */
-static v3 shading_normal(const attrs_t* a) {
+/* image::read, LIB/image/image.cpp:124-141 */
+static float tex_read(const ptb_texture_desc* T, uint32_t x, uint32_t y, uint32_t c) {
+    uint32_t index = y * T->width + x;
+    index = index * T->channels + c;
+    float value;
+    if (T->is_float) value = ((const float*)T->pixels)[index];
+    else value = ((const uint8_t*)T->pixels)[index] / 255.0F;
+    if (T->srgb && c < 3) value = powf(value, 2.2F);
+    return value;
+}
+typedef struct { float x, y, z, w; } v4;
+/* image_texture::read_pixel, LIB/image/image_texture.cpp:47-62 (missing channels stay 1) */
+static v4 tex_pixel(const ptb_texture_desc* T, uint32_t x, uint32_t y) {
+    v4 c = {1, 1, 1, 1};
+    if (T->channels >= 4) c.w = tex_read(T, x, y, 3);
+    if (T->channels >= 3) c.z = tex_read(T, x, y, 2);
+    if (T->channels >= 2) c.y = tex_read(T, x, y, 1);
+    if (T->channels >= 1) c.x = tex_read(T, x, y, 0);
+    return c;
+}
+static v4 lerp4(v4 a, v4 b, float w) {
+    v4 r = {lerpf(a.x, b.x, w), lerpf(a.y, b.y, w), lerpf(a.z, b.z, w), lerpf(a.w, b.w, w)};
+    return r;
+}
+/* image_texture::sample, LIB/image/image_texture.cpp:21-45: bilinear, wrap-around */
+static v4 tex_sample(const po_scene* s, uint32_t id, float u, float v) {
+    const ptb_texture_desc* T = &s->textures[id];
+    float cx = u * T->width - 0.5F, cy = (1 - v) * T->height - 0.5F;
+    float fx = floorf(cx), fy = floorf(cy), gx = ceilf(cx), gy = ceilf(cy);
+    /* uvec2(float) then math::mod(uvec2, size) = (size + x % size) % size, LIB/math/math.inl:190-196 */
+#define WRAP(f, size) (((size) + ((uint32_t)(int64_t)(f)) % (size)) % (size))
+    uint32_t x0 = WRAP(fx, T->width), x1 = WRAP(gx, T->width), y0 = WRAP(fy, T->height), y1 = WRAP(gy, T->height);
+#undef WRAP
+    float dx = cx - fx, dy = cy - fy; /* math::fract */
+    v4 t = lerp4(tex_pixel(T, x0, y0), tex_pixel(T, x1, y0), dx);
+    v4 b = lerp4(tex_pixel(T, x0, y1), tex_pixel(T, x1, y1), dx);
+    return lerp4(t, b, dy);
+}
+
+/* material::get_normal, LIB/core/material.cpp:6-11 */
+static v3 material_normal(const po_scene* s, uint32_t mat, float u, float v) {
+    const ptb_material_desc* m = &s->materials[mat];
+    if (m->normal_tex != PTB_NO_TEXTURE) {
+        v4 c = tex_sample(s, m->normal_tex, u, v);
+        return sub(muls(V(c.x, c.y, c.z), 2), V(1, 1, 1));
+    }
+    return V(0, 0, 1);
+}
+
+/* intersect_result::get_normal, LIB/core/renderer.cpp:430-435 */
+static v3 shading_normal_s(const po_scene* s, const attrs_t* a) {
     v3 binormal = cross(a->normal, a->tangent);
     m3 tbn = {a->tangent, binormal, a->normal};
-    return mat_vec(&tbn, V(0, 0, 1));
+    return mat_vec(&tbn, material_normal(s, a->material, a->u, a->v));
 }
 
 void po_trace_rays(const po_scene* s, const float* od, uint64_t n, ptb_hit* hits, float* attrs) {
@@ -649,7 +707,7 @@ void po_trace_rays(const po_scene* s, const float* od, uint64_t n, ptb_hit* hits
             float* a = attrs + 14 * i;
             if (!(h.t >= 0)) { for (int k = 0; k < 14; k++) a[k] = 0; continue; }
             attrs_t at = hit_attrs(s, &h);
-            v3 sn = shading_normal(&at);
+            v3 sn = shading_normal_s(s, &at);
             a[0] = at.position.x; a[1] = at.position.y; a[2] = at.position.z; a[3] = at.u; a[4] = at.v;
             a[5] = at.normal.x; a[6] = at.normal.y; a[7] = at.normal.z;
             a[8] = at.tangent.x; a[9] = at.tangent.y; a[10] = at.tangent.z;
@@ -794,12 +852,20 @@ static void rng_seed(rng_t* g, uint64_t seed) {
 
 typedef struct { v3 rgb; float alpha; } rgba_t;
 typedef struct { v3 albedo; float opacity, roughness, metallic; v3 emissive; float ior; int shadow_catcher; } mat_t;
-static mat_t material_of(const po_scene* s, uint32_t id) { /* LIB/core/material.cpp:13-53 without textures */
+static mat_t material_of(const po_scene* s, uint32_t id, float u, float v) { /* LIB/core/material.cpp:13-53 */
     const ptb_material_desc* m = &s->materials[id];
     mat_t r;
     r.albedo = V(m->albedo[0], m->albedo[1], m->albedo[2]);
-    r.opacity = m->opacity; r.roughness = m->roughness; r.metallic = m->metallic;
-    r.emissive = muls(V(m->emissive[0], m->emissive[1], m->emissive[2]), 10); /* renderer.cpp:462 */
+    if (m->albedo_tex != PTB_NO_TEXTURE) { v4 c = tex_sample(s, m->albedo_tex, u, v); r.albedo = mulv(r.albedo, V(c.x, c.y, c.z)); }
+    r.opacity = m->opacity;
+    if (m->opacity_tex != PTB_NO_TEXTURE) r.opacity *= tex_sample(s, m->opacity_tex, u, v).w;
+    r.roughness = m->roughness;
+    if (m->roughness_tex != PTB_NO_TEXTURE) r.roughness *= tex_sample(s, m->roughness_tex, u, v).y;
+    r.metallic = m->metallic;
+    if (m->metallic_tex != PTB_NO_TEXTURE) r.metallic *= tex_sample(s, m->metallic_tex, u, v).z;
+    r.emissive = V(m->emissive[0], m->emissive[1], m->emissive[2]);
+    if (m->emissive_tex != PTB_NO_TEXTURE) { v4 c = tex_sample(s, m->emissive_tex, u, v); r.emissive = mulv(r.emissive, V(c.x, c.y, c.z)); }
+    r.emissive = muls(r.emissive, 10); /* renderer.cpp:462 */
     r.ior = m->ior; r.shadow_catcher = m->shadow_catcher != 0;
     return r;
 }
@@ -825,10 +891,10 @@ static rgba_t trace_lib(const po_scene* s, uint32_t bounce, uint32_t bounce_coun
     scene_hit h = scene_intersect(s, &r, NULL);
     if (!(h.t >= 0)) { rgba_t e = {s->environment, s->transparent ? 0.0f : 1.0f}; return e; }
     attrs_t at = hit_attrs(s, &h);
-    mat_t m = material_of(s, at.material);
+    mat_t m = material_of(s, at.material, at.u, at.v);
     if (!is_approx(m.opacity, 1) && rnd(g) > m.opacity)
         return trace_lib(s, bounce, bounce_count, make_ray(add(at.position, muls(r.d, EPS)), r.d), g);
-    v3 normal = shading_normal(&at);
+    v3 normal = shading_normal_s(s, &at);
     v3 outcoming = neg(r.d);
     if (dot(normal, outcoming) <= 0) return future;
     float roughness = fmaxr(m.roughness, 0.05F);
@@ -881,13 +947,13 @@ static rgba_t trace_app(const po_scene* s, uint32_t initial_bounce, ray cur, rng
         }
         alpha = 1.0f;
         attrs_t at = hit_attrs(s, &h);
-        mat_t m = material_of(s, at.material);
+        mat_t m = material_of(s, at.material, at.u, at.v);
         acc = add(acc, mulv(thr, m.emissive));
         if (!is_approx(m.opacity, 1) && rnd(g) > m.opacity) {
             cur = make_ray(add(at.position, muls(cur.d, EPS)), cur.d);
             continue;
         }
-        v3 normal = shading_normal(&at);
+        v3 normal = shading_normal_s(s, &at);
         v3 outcoming = neg(cur.d);
         if (dot(normal, outcoming) <= 0) break;
         if (m.shadow_catcher && bounce_remaining == initial_bounce) {

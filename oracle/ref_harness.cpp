@@ -22,6 +22,7 @@
 #include "path_tracer/core/utils.hpp"
 #include "path_tracer/geometry/ray.hpp"
 #include "path_tracer/image/image.hpp"
+#include "path_tracer/image/image_texture.hpp"
 #include "path_tracer/scene/model.hpp"
 #include "path_tracer/util/rand_cone_vec.hpp"
 
@@ -48,6 +49,8 @@ struct ref_scene {
     std::map<const core::material*, uint32_t> material_id;
     std::map<const scene::model::surface*, std::pair<uint32_t, uint32_t>> surface_id; // → (instance, ordinal)
     std::vector<std::shared_ptr<scene::entity>> keep_alive;
+    std::vector<const ::image::texture*> textures; // unique, first-appearance order over the materials' slots
+    std::map<const ::image::texture*, uint32_t> texture_id;
 };
 
 // Enumerate entities in exactly the order renderer::intersect visits them
@@ -79,6 +82,15 @@ void index_scene(ref_scene& s) {
             if (!s.material_id.count(surf.material.get())) {
                 s.material_id[surf.material.get()] = static_cast<uint32_t>(s.materials.size());
                 s.materials.push_back(surf.material.get());
+                const core::material& m = *surf.material;
+                // occlusion_tex is loaded by the reference but never sampled by the integrators: not exported
+                for (const auto& t : {m.normal_tex, m.albedo_tex, m.opacity_tex, m.roughness_tex, m.metallic_tex,
+                                      m.emissive_tex}) {
+                    if (t && !s.texture_id.count(t.get())) {
+                        s.texture_id[t.get()] = static_cast<uint32_t>(s.textures.size());
+                        s.textures.push_back(t.get());
+                    }
+                }
             }
         }
     }
@@ -378,8 +390,7 @@ void* ref_scene_from_gltf(const char* path, uint32_t camera_index, uint32_t sun_
 // Builds reference entities/models/meshes from a flat description
 // (recipe: SURVEY.md appendix B).  Instances become children of one root
 // entity, attached in reverse so that renderer::intersect visits them in
-// array order.  Textures are not supported here (fixtures with textures come
-// from ref_scene_from_gltf).
+// array order.  Textures become image::image_texture objects over a copy of the pixels.
 void* ref_scene_from_desc(const ptb_scene_desc* d) {
     silence_cout quiet;
     auto* s = new ref_scene;
@@ -402,10 +413,28 @@ void* ref_scene_from_desc(const ptb_scene_desc* d) {
         mesh->build_kd_tree(d->kd_use_sah != 0, d->kd_max_depth ? d->kd_max_depth : 25);
         meshes.push_back(mesh);
     }
+    std::vector<std::shared_ptr<::image::texture>> textures;
+    for (uint32_t t = 0; t < d->n_textures; t++) {
+        const ptb_texture_desc& td = d->textures[t];
+        auto img = std::make_shared<::image::image>(uvec2(td.width, td.height), td.channels, td.is_float != 0,
+                                                    td.srgb != 0);
+        const size_t bytes = size_t(td.width) * td.height * td.channels * (td.is_float ? 4 : 1);
+        memcpy(img->data.data(), td.pixels, bytes); // private member; this TU is built with -fno-access-control
+        textures.push_back(std::make_shared<::image::image_texture>(img));
+    }
+    auto tex = [&](uint32_t id) -> std::shared_ptr<::image::texture> {
+        return id == PTB_NO_TEXTURE ? nullptr : textures[id];
+    };
     std::vector<std::shared_ptr<core::material>> materials;
     for (uint32_t m = 0; m < d->n_materials; m++) {
         const ptb_material_desc& md = d->materials[m];
         auto mat = std::make_shared<core::material>();
+        mat->normal_tex = tex(md.normal_tex);
+        mat->albedo_tex = tex(md.albedo_tex);
+        mat->opacity_tex = tex(md.opacity_tex);
+        mat->roughness_tex = tex(md.roughness_tex);
+        mat->metallic_tex = tex(md.metallic_tex);
+        mat->emissive_tex = tex(md.emissive_tex);
         mat->albedo_fac = fvec3(md.albedo[0], md.albedo[1], md.albedo[2]);
         mat->opacity_fac = md.opacity;
         mat->roughness_fac = md.roughness;
@@ -542,8 +571,15 @@ void ref_export_materials(void* h, ptb_material_desc* out, uint32_t* tex_mask) {
         o.emissive[0] = m.emissive_fac.x; o.emissive[1] = m.emissive_fac.y; o.emissive[2] = m.emissive_fac.z;
         o.ior = m.ior;
         o.shadow_catcher = m.shadow_catcher;
-        o.normal_tex = o.albedo_tex = o.opacity_tex = o.roughness_tex = o.metallic_tex = o.emissive_tex =
-            PTB_NO_TEXTURE;
+        auto tid = [&](const std::shared_ptr<::image::texture>& t) -> uint32_t {
+            return t ? s->texture_id[t.get()] : PTB_NO_TEXTURE;
+        };
+        o.normal_tex = tid(m.normal_tex);
+        o.albedo_tex = tid(m.albedo_tex);
+        o.opacity_tex = tid(m.opacity_tex);
+        o.roughness_tex = tid(m.roughness_tex);
+        o.metallic_tex = tid(m.metallic_tex);
+        o.emissive_tex = tid(m.emissive_tex);
         if (tex_mask)
             tex_mask[i] = (m.normal_tex ? 1u : 0u) | (m.albedo_tex ? 2u : 0u) | (m.opacity_tex ? 4u : 0u) |
                           (m.roughness_tex ? 8u : 0u) | (m.metallic_tex ? 16u : 0u) |
@@ -566,6 +602,22 @@ void ref_export_globals(void* h, ptb_camera_desc* cam, ptb_sun_desc* sun, float*
     }
     env3[0] = s->r.environment_factor.x; env3[1] = s->r.environment_factor.y; env3[2] = s->r.environment_factor.z;
     *transparent = s->r.transparent_background;
+}
+
+uint32_t ref_export_texture_count(void* h) { return static_cast<uint32_t>(static_cast<ref_scene*>(h)->textures.size()); }
+
+// info5 = width, height, channels, is_float, srgb
+void ref_export_texture_info(void* h, uint32_t id, uint32_t* info5) {
+    auto* s = static_cast<ref_scene*>(h);
+    auto* it = static_cast<const ::image::image_texture*>(s->textures[id]);
+    const ::image::image& img = *it->img;
+    info5[0] = img.size.x; info5[1] = img.size.y; info5[2] = img.channel_count; info5[3] = img.hdr; info5[4] = img.srgb;
+}
+
+void ref_export_texture_data(void* h, uint32_t id, void* out) {
+    auto* s = static_cast<ref_scene*>(h);
+    auto* it = static_cast<const ::image::image_texture*>(s->textures[id]);
+    memcpy(out, it->img->data.data(), it->img->data.size());
 }
 
 // ---- KD tree serialisation (same record stream as ptb_scene_dump_kd) ----------

@@ -201,6 +201,10 @@ def lib():
         L.ref_export_surfaces.argtypes = [C.c_void_p, C.POINTER(SurfaceDesc)]
         L.ref_export_instances.argtypes = [C.c_void_p, C.POINTER(InstanceDesc), f32p]
         L.ref_export_materials.argtypes = [C.c_void_p, C.POINTER(MaterialDesc), u32p]
+        L.ref_export_texture_count.restype = C.c_uint32
+        L.ref_export_texture_count.argtypes = [C.c_void_p]
+        L.ref_export_texture_info.argtypes = [C.c_void_p, C.c_uint32, u32p]
+        L.ref_export_texture_data.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.ref_export_globals.argtypes = [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(SunDesc), f32p, u32p]
         L.ref_dump_kd.restype = C.c_int
         L.ref_dump_kd.argtypes = [C.c_void_p, C.c_uint32, u32p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -277,7 +281,17 @@ class RefScene:
         L.ref_export_materials(self.h, mat, _up(mask))
         materials = [dict(albedo=tuple(m.albedo), opacity=m.opacity, roughness=m.roughness,
                           metallic=m.metallic, emissive=tuple(m.emissive), ior=m.ior,
-                          shadow_catcher=m.shadow_catcher) for m in mat]
+                          shadow_catcher=m.shadow_catcher, normal_tex=m.normal_tex, albedo_tex=m.albedo_tex,
+                          opacity_tex=m.opacity_tex, roughness_tex=m.roughness_tex, metallic_tex=m.metallic_tex,
+                          emissive_tex=m.emissive_tex) for m in mat]
+        textures = []
+        for t in range(L.ref_export_texture_count(self.h)):
+            info = np.zeros(5, np.uint32)
+            L.ref_export_texture_info(self.h, t, _up(info))
+            w, h, c, is_float, srgb = (int(x) for x in info)
+            px = np.empty((h, w, c), np.float32 if is_float else np.uint8)
+            L.ref_export_texture_data(self.h, t, px.ctypes.data)
+            textures.append(dict(pixels=px, srgb=bool(srgb)))
         cam, sun = CameraDesc(), SunDesc()
         env = np.empty(3, np.float32)
         tr = C.c_uint32()
@@ -285,7 +299,7 @@ class RefScene:
         flat = FlatScene(meshes, surfaces, instances, materials,
                          (list(cam.origin), list(cam.basis), cam.yfov),
                          (list(sun.basis), list(sun.energy), sun.angular_radius) if sun.enabled else None,
-                         tuple(env), bool(tr.value))
+                         tuple(env), bool(tr.value), textures=textures)
         flat.texture_masks = mask
         flat.model_aabbs = maabb
         flat.mesh_aabbs = [m["aabb"] for m in meshes]

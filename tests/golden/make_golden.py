@@ -47,6 +47,13 @@ def flat_to_npz(flat):
     d["inst_range"] = np.array([(i[2], i[3]) for i in flat.instances], np.uint32)
     d["materials"] = np.array([[*m["albedo"], m["opacity"], m["roughness"], m["metallic"], *m["emissive"], m["ior"],
                                 float(m.get("shadow_catcher", 0))] for m in flat.materials], np.float32)
+    d["material_tex"] = np.array([[m.get(k + "_tex", 0xFFFFFFFF) for k in
+                                   ("normal", "albedo", "opacity", "roughness", "metallic", "emissive")]
+                                  for m in flat.materials], np.uint32)
+    d["n_textures"] = np.array(len(flat.textures))
+    for i, t in enumerate(flat.textures):
+        d[f"tex{i}_pixels"] = np.ascontiguousarray(t["pixels"])
+        d[f"tex{i}_srgb"] = np.array(int(bool(t.get("srgb", False))))
     d["camera_origin"], d["camera_basis"] = flat.camera[0], flat.camera[1]
     d["camera_yfov"] = np.array(flat.camera[2], np.float32)
     if flat.sun is not None:
@@ -124,6 +131,68 @@ def main():
     d = flat_to_npz(sun_scene)
     d.update(ray_sets(sr, 64, 48, 4096, (-4, -1, -4), (4, 4, 7)))
     np.savez_compressed(os.path.join(HERE, "sun_scene_rays.npz"), **d)
+
+    # --- jack-of-blades: the reference's organic fixture (58 740 triangles, 7 meshes, 12-14x leaf duplication).
+    # Geometry only travels (2 MB); its 20 MB of textures stay in the reference tree, texture parity is covered by
+    # the synthetic scene below and, where /root/reference exists, by tests/test_host.py on the real files.
+    jack_gltf = "/root/reference/path-tracer-core/scenes/jack-of-blades/jack-of-blades.gltf"
+    if os.path.exists(jack_gltf):
+        jf = reflib.RefScene.from_gltf(jack_gltf).export_flat()
+        for m in jf.materials:
+            for k in ("normal", "albedo", "opacity", "roughness", "metallic", "emissive"):
+                m[k + "_tex"] = 0xFFFFFFFF
+        jf.textures = []
+        jr = reflib.RefScene.from_flat(jf)
+        d = flat_to_npz(jf)
+        d.update(ray_sets(jr, 96, 54, 8192, (-3, -1, -3), (3, 5, 6)))
+        d["kd_words"] = np.array([len(jr.dump_kd(i)) for i in range(len(jf.meshes))], np.uint64)
+        d["kd_crc"] = np.array([int(np.bitwise_xor.reduce(jr.dump_kd(i) * np.arange(1, len(jr.dump_kd(i)) + 1, dtype=np.uint32)))
+                                for i in range(len(jf.meshes))], np.uint64)
+        np.savez_compressed(os.path.join(HERE, "jack_geometry_rays.npz"), **d)
+
+    # --- synthetic textured scene: every material slot, sRGB + linear + float textures, alpha-tested opacity,
+    # normal mapping, a scaled/rotated second instance, a sun
+    trng = np.random.default_rng(77)
+    def blobs(h, w, c, lo=0, hi=256):
+        base = trng.integers(lo, hi, (h // 4 + 1, w // 4 + 1, c)).astype(np.float32)
+        img = np.kron(base, np.ones((4, 4, 1), np.float32))[:h, :w]
+        return np.clip(img + trng.normal(0, 6, (h, w, c)), 0, 255).astype(np.uint8)
+    albedo = blobs(32, 32, 4, 40, 256)
+    albedo[..., 3] = np.where(trng.random((32, 32)) < 0.25, 90, 255).astype(np.uint8)   # holes: opacity 0.35
+    nrm = blobs(16, 16, 3, 96, 160)
+    nrm[..., 2] = 255
+    rough_metal = blobs(8, 8, 3, 30, 220)
+    emis = (trng.random((8, 8, 3)) ** 6).astype(np.float32) * np.float32(0.6)                 # float texture
+    textures = [dict(pixels=albedo, srgb=True), dict(pixels=nrm, srgb=False), dict(pixels=rough_metal, srgb=False),
+                dict(pixels=emis, srgb=False), dict(pixels=blobs(20, 12, 3, 0, 256), srgb=True)]
+    ground = P.heightfield_mesh(10, 2.0, 5)
+    ground["positions"][:, 1] *= 0.35
+    NT = 0xFFFFFFFF
+    tmats = [dict(albedo=(0.9, 0.9, 0.9), opacity=1.0, roughness=0.9, metallic=0.8, emissive=(0.0, 0.0, 0.0), ior=1.33,
+                  normal_tex=1, albedo_tex=0, opacity_tex=0, roughness_tex=2, metallic_tex=2, emissive_tex=NT),
+             dict(albedo=(0.7, 0.8, 1.0), opacity=0.6, roughness=0.4, metallic=0.1, emissive=(1.0, 0.9, 0.8), ior=1.33,
+                  normal_tex=NT, albedo_tex=4, opacity_tex=NT, roughness_tex=NT, metallic_tex=NT, emissive_tex=3)]
+    tinst = [((0.0, 0.0, 0.0), P.IDENTITY, 0, 1),
+             ((0.3, 0.9, -0.6), rot_y(0.9, (0.45, 1.6, 0.45)), 1, 1)]
+    tcam_o, tcam_b = P.look_at((0.4, 2.2, 3.4), (0.05, 0.2, 0))
+    tsun_o, tsun_b = P.look_at((0.8, 2.0, 1.1), (0, 0, 0))
+    tscene = reflib.FlatScene([ground], [(0, 0), (0, 1)], tinst, tmats, (tcam_o, tcam_b, 0.75),
+                              sun=(tsun_b, (2.5, 2.3, 2.0), 0.004732), environment_factor=(0.5, 0.6, 0.8),
+                              textures=textures)
+    tr = reflib.RefScene.from_flat(tscene)
+    d = flat_to_npz(tscene)
+    d.update(ray_sets(tr, 64, 48, 4096, (-2.5, -0.5, -2.5), (2.5, 3, 3.5)))
+    for name, mode, depth in (("A", 0, 4), ("B", 1, 6)):
+        acc = np.zeros((48, 64, 3), np.float64); acc2 = np.zeros((48, 64, 3), np.float64); nb = 24
+        for b in range(nb):
+            rgb64, _, _, _ = tr.render_linear(64, 48, 64, depth, mode=mode)
+            acc += rgb64; acc2 += rgb64.astype(np.float64) ** 2
+        mean = acc / nb
+        d[f"converged_{name}_mean"] = mean.astype(np.float32)
+        d[f"converged_{name}_sigma"] = np.sqrt(np.maximum(acc2 / nb - mean ** 2, 0) * nb / (nb - 1) * 64).astype(np.float32)
+        d[f"converged_{name}_spp"] = np.array(64 * nb)
+        d[f"converged_{name}_depth"] = np.array(depth)
+    np.savez_compressed(os.path.join(HERE, "textured_scene_rays.npz"), **d)
 
     # --- tonemap
     rgb = np.concatenate([rng.random((4096, 3), dtype=np.float32) * np.float32(4.0),

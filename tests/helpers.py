@@ -17,17 +17,24 @@ def scene_parts_from_npz(z):
             for i in range(len(z["inst_origin"]))]
     mats = [dict(albedo=tuple(m[0:3]), opacity=float(m[3]), roughness=float(m[4]), metallic=float(m[5]),
                  emissive=tuple(m[6:9]), ior=float(m[9]), shadow_catcher=int(m[10])) for m in z["materials"]]
+    if "material_tex" in z:
+        for m, ids in zip(mats, z["material_tex"]):
+            for k, v in zip(("normal", "albedo", "opacity", "roughness", "metallic", "emissive"), ids):
+                m[k + "_tex"] = int(v)
+    textures = [dict(pixels=z[f"tex{i}_pixels"], srgb=bool(z[f"tex{i}_srgb"]))
+                for i in range(int(z["n_textures"]))] if "n_textures" in z else []
     sun = (z["sun_basis"], z["sun_energy"], float(z["sun_angular_radius"])) if "sun_basis" in z else None
     cam = (z["camera_origin"], z["camera_basis"], float(z["camera_yfov"]))
     return dict(meshes=meshes, surfaces=z["surfaces"], instances=inst, materials=mats, camera=cam, sun=sun,
                 environment_factor=tuple(float(x) for x in z["environment_factor"]),
-                transparent_background=bool(z["transparent_background"]))
+                transparent_background=bool(z["transparent_background"]), textures=textures)
 
 
 def make_flat(cls, parts):
     """cls: reflib.FlatScene or ptb.SceneDescription (same constructor)."""
     return cls(parts["meshes"], parts["surfaces"], parts["instances"], parts["materials"], parts["camera"],
-               parts["sun"], parts["environment_factor"], parts["transparent_background"])
+               parts["sun"], parts["environment_factor"], parts["transparent_background"],
+               textures=parts.get("textures", ()))
 
 
 def bits(a):

@@ -74,6 +74,50 @@ def test_transformed_instances_and_sun_scene(ptb):
             assert np.array_equal(H.bits(attrs), H.bits(z[key + "_attrs"]))
 
 
+def test_jack_of_blades_geometry(ptb):
+    """The reference's organic scene (58 740 triangles, 7 meshes in 7 instances): trees + hits + attributes."""
+    z = H.load("jack_geometry_rays.npz")
+    with ptb.Scene.create(H.make_flat(ptb.SceneDescription, H.scene_parts_from_npz(z))) as s:
+        for m in range(int(z["n_meshes"])):
+            w = s.dump_kd(m)
+            crc = int(np.bitwise_xor.reduce(w * np.arange(1, len(w) + 1, dtype=np.uint32)))
+            assert len(w) == int(z["kd_words"][m]) and crc == int(z["kd_crc"][m])
+        for key in ("cam", "rnd", "bounce"):
+            hits, attrs = s.trace_rays(z[key + "_rays"], attrs=True)
+            H.assert_hits_equal(hits, z[key + "_hits"], "jack:" + key)
+            assert np.array_equal(H.bits(attrs), H.bits(z[key + "_attrs"]))
+
+
+def test_textured_scene_hits_and_normal_mapping(ptb):
+    """Shading normals through the bilinear, wrapping normal-map sample: bit-exact with the reference."""
+    z = H.load("textured_scene_rays.npz")
+    with ptb.Scene.create(H.make_flat(ptb.SceneDescription, H.scene_parts_from_npz(z))) as s:
+        assert s.info()["n_textures"] == 5
+        for key in ("cam", "rnd", "bounce"):
+            hits, attrs = s.trace_rays(z[key + "_rays"], attrs=True)
+            H.assert_hits_equal(hits, z[key + "_hits"], "textured:" + key)
+            assert np.array_equal(H.bits(attrs), H.bits(z[key + "_attrs"])), key
+
+
+@pytest.mark.parametrize("name,mode", [("A", 0), ("B", 1)])
+def test_textured_scene_image_statistics(ptb, name, mode):
+    """sRGB / linear / float textures, alpha holes (stochastic opacity, extra wavefront iterations), factor
+    opacity, metallic-roughness maps, emissive map, sun + shadow rays: image mean within 4.5 sigma of the
+    reference's converged image (sigma: the reference's per-pixel sample deviation, both runs' noise pooled)."""
+    z = H.load("textured_scene_rays.npz")
+    conv = dict(mean=z[f"converged_{name}_mean"], sigma_per_sample=z[f"converged_{name}_sigma"],
+                spp=z[f"converged_{name}_spp"])
+    spp = 1024
+    with ptb.Scene.create(H.make_flat(ptb.SceneDescription, H.scene_parts_from_npz(z))) as s:
+        rgb, alpha, st = s.render_tile(64, 48, spp, int(z[f"converged_{name}_depth"]), seed=21, integrator=mode)
+    assert not np.isnan(rgb).any()
+    zs = H.mean_z(rgb, conv, spp) / np.sqrt(1 + spp / float(conv["spp"]))
+    assert np.all(np.abs(zs) < 4.5), zs
+    se = conv["sigma_per_sample"] * np.sqrt(1.0 / spp + 1.0 / float(conv["spp"])) + 2e-3
+    dev = np.abs(rgb - conv["mean"]) / se
+    assert np.quantile(dev, 0.99) < 5.0, np.quantile(dev, 0.99)
+
+
 def test_heightfield_golden_and_visit_counts(ptb, procedural):
     with ptb.Scene.create(procedural.heightfield_scene(40)) as s:
         kd = H.load("heightfield40_kd.npz")

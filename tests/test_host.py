@@ -125,6 +125,30 @@ def test_gltf_loader_reproduces_reference_scene(ptb, procedural):
     assert got.sun is None
 
 
+def test_gltf_and_png_loader_on_jack_of_blades(ptb, reflib):
+    """Only where the reference tree is mounted: the textured fixture (17 PNG textures, KHR_lights_punctual sun,
+    BLEND materials) loaded by gltf.cpp + png.cpp against the reference's cgltf + stb_image load."""
+    path = "/root/reference/path-tracer-core/scenes/jack-of-blades/jack-of-blades.gltf"
+    if not (os.path.exists(path) and reflib.available()):
+        pytest.skip("reference tree or oracle/_ref not present")
+    want = reflib.RefScene.from_gltf(path).export_flat()
+    got = ptb.load_gltf_description(path)
+    assert len(got.meshes) == len(want.meshes) == 7 and len(got.textures) == len(want.textures) == 17
+    for a, b in zip(got.meshes, want.meshes):
+        for k in H.MESH_KEYS:
+            assert np.array_equal(H.bits(a[k]), H.bits(b[k])), k
+    assert np.array_equal(got.surfaces, want.surfaces)
+    for a, b in zip(got.instances, want.instances):
+        assert np.array_equal(H.bits(a[0]), H.bits(b[0])) and np.array_equal(H.bits(a[1]), H.bits(b[1])) and a[2:] == b[2:]
+    for a, b in zip(got.materials, want.materials):
+        for k in b:
+            assert np.all(np.float32(a[k]) == np.float32(b[k])), k
+    for a, b in zip(got.textures, want.textures):
+        assert a["srgb"] == b["srgb"] and np.array_equal(a["pixels"], b["pixels"])
+    assert got.sun is not None and np.allclose(got.sun[1], want.sun[1]) and np.array_equal(
+        np.float32(got.sun[0]), np.float32(want.sun[0]))
+
+
 def test_gltf_loader_errors(ptb, tmp_path):
     bad = tmp_path / "bad.gltf"
     bad.write_text("{ not json")

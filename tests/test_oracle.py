@@ -6,7 +6,8 @@ import pytest
 
 import helpers as H
 
-SCENES = [("cornell_scene.npz", "cornell_rays.npz"), ("sun_scene_rays.npz", "sun_scene_rays.npz")]
+SCENES = [("cornell_scene.npz", "cornell_rays.npz"), ("sun_scene_rays.npz", "sun_scene_rays.npz"),
+          ("textured_scene_rays.npz", "textured_scene_rays.npz"), ("jack_geometry_rays.npz", "jack_geometry_rays.npz")]
 
 
 @pytest.fixture(scope="module")
@@ -29,6 +30,32 @@ def test_port_closest_hits_bit_exact(portlib, reflib, scene_file, ray_file):
         hits, attrs = ps.trace_rays(r[key + "_rays"], attrs=True)
         H.assert_hits_equal(hits, r[key + "_hits"], f"{scene_file}:{key}")
         assert np.array_equal(H.bits(attrs), H.bits(r[key + "_attrs"])), f"{key}: attributes differ"
+
+
+def kd_crc(words):
+    return int(np.bitwise_xor.reduce(words * np.arange(1, len(words) + 1, dtype=np.uint32)))
+
+
+def test_port_jack_of_blades_trees(portlib, reflib):
+    """The organic fixture: 7 meshes, 58 740 triangles; tree length + checksum of the reference's trees."""
+    z = H.load("jack_geometry_rays.npz")
+    ps = portlib.PortScene(H.make_flat(reflib.FlatScene, H.scene_parts_from_npz(z)))
+    for m in range(int(z["n_meshes"])):
+        w = ps.dump_kd(m)
+        assert len(w) == int(z["kd_words"][m]) and kd_crc(w) == int(z["kd_crc"][m]), f"mesh {m}"
+
+
+@pytest.mark.parametrize("name,mode", [("A", 0), ("B", 1)])
+def test_port_textured_scene_image_statistics(portlib, reflib, name, mode):
+    """Textures (sRGB / linear / float), normal map, alpha holes, factor opacity, sun + shadow rays."""
+    z = H.load("textured_scene_rays.npz")
+    ps = portlib.PortScene(H.make_flat(reflib.FlatScene, H.scene_parts_from_npz(z)))
+    conv = dict(mean=z[f"converged_{name}_mean"], sigma_per_sample=z[f"converged_{name}_sigma"],
+                spp=z[f"converged_{name}_spp"])
+    spp = 256
+    rgb, alpha, rays, _ = ps.render_linear(64, 48, spp, int(z[f"converged_{name}_depth"]), mode=mode, seed=5, threads=4)
+    zs = H.mean_z(rgb, conv, spp) / np.sqrt(1 + spp / float(conv["spp"]))
+    assert np.all(np.abs(zs) < 4.5), zs
 
 
 def test_port_heightfield(portlib, reflib, procedural):
