@@ -122,7 +122,7 @@ HIT_DTYPE = np.dtype([("instance", "<u4"), ("surface", "<u4"), ("triangle", "<u4
 EXPORTS = [
     "ptb_scene_create", "ptb_scene_load_gltf", "ptb_scene_destroy", "ptb_scene_get_info", "ptb_scene_dump_kd",
     "ptb_trace_rays", "ptb_trace_rays_attrs", "ptb_render_tile", "ptb_render_tile_dev", "ptb_tonemap_rgba8",
-    "ptb_write_png", "ptb_host_build_kd", "ptb_desc_load_gltf", "ptb_desc_get", "ptb_desc_free",
+    "ptb_write_png", "ptb_worker_run", "ptb_host_build_kd", "ptb_desc_load_gltf", "ptb_desc_get", "ptb_desc_free",
     "ptb_camera_rays", "ptb_trace_rays_stats", "ptb_extend_registers", "ptb_selftest_division", "ptb_set_option", "ptb_last_error",
     "ptb_abi_version", "ptb_device_count",
 ]
@@ -167,6 +167,9 @@ def lib():
     L.ptb_tonemap_rgba8.argtypes = [f32p, f32p, C.c_uint64, C.c_void_p]
     L.ptb_write_png.restype = st
     L.ptb_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.ptb_worker_run.restype = st
+    L.ptb_worker_run.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, u32p, u32p,
+                                 C.POINTER(RenderStats)]
     L.ptb_host_build_kd.restype = st
     L.ptb_host_build_kd.argtypes = [f32p, C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                     u32p, C.c_uint64, C.POINTER(C.c_uint64), f32p]
@@ -534,6 +537,22 @@ class Renderer:
         """→ RGBA8 image [h,w,4], what the reference encodes into its PNG."""
         rgb, alpha = self.render_linear()
         return tonemap_rgba8(rgb, alpha)
+
+
+def worker_run(worker_info, scene_dir, device=0, png_path=None):
+    """The Lambda worker's entry: ``worker_info`` (dict or JSON text, the preprocessor's payload) in, RGBA8 image
+    out (+ the PNG the worker would upload as test.png when ``png_path`` is given).  → (rgba8[h,w,4], stats)."""
+    import json as _json
+    text = worker_info if isinstance(worker_info, str) else _json.dumps(worker_info)
+    d = _json.loads(text)
+    w, h = int(float(d.get("X", 640))), int(float(d.get("Y", 480)))
+    out = np.empty((h, w, 4), np.uint8)
+    wo, ho, st = C.c_uint32(), C.c_uint32(), RenderStats()
+    _check(lib().ptb_worker_run(text.encode(), os.fsencode(scene_dir), device,
+                                os.fsencode(png_path) if png_path else None, out.ctypes.data, C.byref(wo),
+                                C.byref(ho), C.byref(st)))
+    assert (wo.value, ho.value) == (w, h)
+    return out, st.as_dict()
 
 
 def worker_render(scene: Scene, samples: int, bounces: int, X: int, Y: int, tile=None, seed=1,

@@ -5,7 +5,11 @@
 #include <exception>
 #include <string>
 
+#include <fstream>
+#include <functional>
+
 #include "errors.hpp"
+#include "json.hpp"
 #include "kd_build.hpp"
 #include "kernels.hpp"
 #include "render.hpp"
@@ -221,6 +225,67 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else {
             throw ptb::Error(PTB_E_INVALID, "unknown option: " + n);
         }
+    });
+}
+
+// The Lambda worker's entry (my_handler → worker::run, APP/main.cpp:9-31, APP/processors/worker/worker.cpp:25-105)
+// without the S3 hops: the request is the worker_info JSON the preprocessor sends, the scene is read from a local
+// mirror of s3://scene_bucket/scene_root.
+ptb_status ptb_worker_run(const char* worker_info_json, const char* scene_dir, int device, const char* png_path,
+                          uint8_t* rgba8_out, uint32_t* width_out, uint32_t* height_out, ptb_render_stats* stats_out) {
+    return guarded([&] {
+        if (!worker_info_json || !scene_dir) throw ptb::Error(PTB_E_INVALID, "worker_info_json or scene_dir is NULL");
+        ptb::Json info;
+        try {
+            const std::string text(worker_info_json);
+            info = ptb::JsonParser(text).parse();
+        } catch (const std::exception& e) {
+            throw ptb::Error(PTB_E_INVALID, std::string("worker_info: ") + e.what());
+        }
+        if (info.kind != ptb::Json::Object) throw ptb::Error(PTB_E_INVALID, "worker_info: not a JSON object");
+        // models::worker_info (APP/models/work_info.hpp:17-31); the preprocessor omits samples/bounces/X/Y
+        // (PRE/app.py:119-127), in which case the worker's own defaults apply (worker.hpp:20-24)
+        ptb::WorkFilter work;
+        if (const ptb::Json* si = info.find("scene_info"))
+            if (const ptb::Json* w = si->find("work"))
+                for (const auto& kv : w->obj) {
+                    std::vector<int>& v = work[kv.first];
+                    for (const ptb::Json& p : kv.second.arr) v.push_back(static_cast<int>(p.number(-1)));
+                }
+        const uint32_t samples = static_cast<uint32_t>(info.get("samples", 50.0));
+        const uint32_t bounces = static_cast<uint32_t>(info.get("bounces", 10.0));
+        const uint32_t X = static_cast<uint32_t>(static_cast<float>(info.get("X", 640.0)));
+        const uint32_t Y = static_cast<uint32_t>(static_cast<float>(info.get("Y", 480.0)));
+        if (!X || !Y || bounces > 255) throw ptb::Error(PTB_E_INVALID, "worker_info: bad X / Y / bounces");
+        const std::string worker_id = info.get("worker_id", std::string("0"));
+
+        std::string gltf = std::string(scene_dir) + "/scene.gltf"; // worker::download_gltf_file: scene_root + "scene.gltf"
+        if (!std::ifstream(gltf).good()) throw ptb::Error(PTB_E_IO, "cannot open " + gltf);
+        ptb::OwnedScene owned;
+        ptb::load_gltf(gltf, 0, 0, owned, info.has("scene_info") ? &work : nullptr);
+        ptb_scene* scene = ptb::create_scene(owned.view(), device);
+        try {
+            ptb_tile_req req{};
+            req.full_w = req.w = X;
+            req.full_h = req.h = Y;
+            req.spp = samples;
+            req.max_depth = bounces;
+            req.seed = std::hash<std::string>{}(worker_id);
+            req.integrator = PTB_INTEGRATOR_APP_RR;
+            req.first_sample_unjittered = 1; // worker::generate_rays, worker.cpp:125-129
+            std::vector<float> rgb(size_t(X) * Y * 3), alpha(size_t(X) * Y);
+            ptb::render_tile_host(scene, req, rgb.data(), alpha.data(), stats_out);
+            std::vector<uint8_t> rgba8(size_t(X) * Y * 4);
+            ptb::tonemap_host(rgb.data(), alpha.data(), size_t(X) * Y, rgba8.data()); // worker::generate_final_image
+            if (png_path) ptb::write_png_rgba8(png_path, rgba8.data(), X, Y);
+            if (rgba8_out) std::memcpy(rgba8_out, rgba8.data(), rgba8.size());
+            if (width_out) *width_out = X;
+            if (height_out) *height_out = Y;
+        } catch (...) {
+            ptb::destroy_scene(scene);
+            throw;
+        }
+        ptb::destroy_scene(scene);
     });
 }
 

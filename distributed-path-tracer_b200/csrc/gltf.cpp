@@ -20,6 +20,7 @@
 //     cached by path only, so the first user decides the sRGB flag (:33-51)
 // Compiled with -ffp-contract=off.
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -197,7 +198,8 @@ float fnum(const Json& j, size_t i, float fallback) {
 
 } // namespace
 
-void load_gltf(const std::string& path, uint32_t camera_index, uint32_t sun_light_index, OwnedScene& out) {
+void load_gltf(const std::string& path, uint32_t camera_index, uint32_t sun_light_index, OwnedScene& out,
+               const WorkFilter* work) {
     Gltf g;
     g.dir = dir_of(path);
     try {
@@ -380,8 +382,16 @@ void load_gltf(const std::string& path, uint32_t camera_index, uint32_t sun_ligh
             e.mesh = static_cast<int>(n.index("mesh"));
             e.has_model = e.mesh >= 0;
             if (e.has_model) { // renderer.cpp:132-143 — primitives before children
-                const Json& prims = gl_meshes.at(static_cast<size_t>(e.mesh)).at("primitives");
+                const Json& gmesh = gl_meshes.at(static_cast<size_t>(e.mesh));
+                const Json& prims = gmesh.at("primitives");
+                const std::vector<int>* keep = nullptr;
+                static const std::vector<int> nothing;
+                if (work) { // APP/scene/load_gltf.cpp:93-100
+                    auto it = work->find(gmesh.get("name", ""));
+                    keep = it == work->end() ? &nothing : &it->second;
+                }
                 for (size_t p = 0; p < prims.size(); p++) {
+                    if (keep && std::find(keep->begin(), keep->end(), static_cast<int>(p)) == keep->end()) continue;
                     ptb_surface_desc sd{};
                     sd.mesh = make_mesh(static_cast<size_t>(e.mesh), p, prims.at(p));
                     sd.material = make_material(prims.at(p));

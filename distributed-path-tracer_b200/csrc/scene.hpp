@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -47,8 +48,12 @@ struct OwnedScene {
     ptb_scene_desc view();
 };
 
-// gltf.cpp — replaces renderer::load_gltf (LIB/core/renderer.cpp:61-331). Throws std::runtime_error.
-void load_gltf(const std::string& path, uint32_t camera_index, uint32_t sun_light_index, OwnedScene& out);
+// gltf.cpp — replaces renderer::load_gltf (LIB/core/renderer.cpp:61-331). Throws ptb::Error.
+// `work` (may be null) is the worker's primitive assignment, mesh name → primitive indices to keep
+// (distributed_scene::process_node, APP/scene/load_gltf.cpp:93-100): a mesh that is not named keeps nothing.
+using WorkFilter = std::map<std::string, std::vector<int>>;
+void load_gltf(const std::string& path, uint32_t camera_index, uint32_t sun_light_index, OwnedScene& out,
+               const WorkFilter* work = nullptr);
 
 // png.cpp
 void write_png_rgba8(const std::string& path, const uint8_t* rgba8, uint32_t w, uint32_t h);

@@ -263,6 +263,23 @@ ptb_status ptb_tonemap_rgba8(const float* rgb, const float* alpha, uint64_t n_pi
 /* image::save_to_memory_png (LIB/image/image.cpp:111-122): RGBA8 → PNG file. */
 ptb_status ptb_write_png(const char* path, const uint8_t* rgba8, uint32_t w, uint32_t h);
 
+/* The Lambda worker's request/response (my_handler → processors::worker::run,
+ * APP/main.cpp:9-31, APP/processors/worker/worker.cpp:25-105) without the S3
+ * hops.  `worker_info_json` is the payload the preprocessor sends
+ * (models::worker_info, APP/models/work_info.hpp:17-31: scene_info.work = mesh
+ * name → primitive indices assigned to this worker, samples, bounces, X, Y, …;
+ * a payload without samples/bounces/X/Y — what PRE/app.py:119-127 really emits —
+ * gets the worker's defaults 50 / 10 / 640 / 480, worker.hpp:20-24).
+ * `scene_dir` is a local mirror of s3://scene_bucket/scene_root and must hold
+ * scene.gltf with its buffers and textures.  Renders with the worker's
+ * integrator (PTB_INTEGRATOR_APP_RR, first sample unjittered), tonemaps as
+ * worker::generate_final_image does, writes the RGBA8 PNG the worker would
+ * upload as "test.png" to `png_path` (may be NULL) and/or copies the RGBA8
+ * pixels to `rgba8_out` (may be NULL; X*Y*4 bytes). */
+ptb_status ptb_worker_run(const char* worker_info_json, const char* scene_dir, int device,
+                          const char* png_path, uint8_t* rgba8_out, uint32_t* width_out,
+                          uint32_t* height_out, ptb_render_stats* stats_out);
+
 /* ------------------------------------------------- host-only / test hooks -- */
 
 /* The build step of ptb_scene_create alone, on the host, without CUDA:

@@ -178,3 +178,16 @@ def test_tile_request_validation_needs_no_gpu(ptb):
     st = ptb.lib().ptb_render_tile(None, ctypes.byref(req), rgb.ctypes.data_as(ptb.f32p), None, None)
     assert st == ptb.PTB_E_INVALID
     assert b"NULL" in ptb.lib().ptb_last_error()
+
+
+def test_worker_request_errors_need_no_gpu(ptb, tmp_path):
+    """worker_info parsing and the scene look-up fail before anything touches CUDA."""
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.worker_run("{ not json", str(tmp_path))
+    assert e.value.status == ptb.PTB_E_INVALID
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.worker_run({"samples": 1, "bounces": 2, "X": 8, "Y": 8}, str(tmp_path / "missing"))
+    assert e.value.status == ptb.PTB_E_IO
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.worker_run({"samples": 1, "bounces": 999, "X": 8, "Y": 8}, str(tmp_path))
+    assert e.value.status == ptb.PTB_E_INVALID
