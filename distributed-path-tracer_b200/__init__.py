@@ -544,8 +544,11 @@ def worker_run(worker_info, scene_dir, device=0, png_path=None):
     out (+ the PNG the worker would upload as test.png when ``png_path`` is given).  → (rgba8[h,w,4], stats)."""
     import json as _json
     text = worker_info if isinstance(worker_info, str) else _json.dumps(worker_info)
-    d = _json.loads(text)
-    w, h = int(float(d.get("X", 640))), int(float(d.get("Y", 480)))
+    try:
+        d = _json.loads(text)
+        w, h = int(float(d.get("X", 640))), int(float(d.get("Y", 480)))
+    except Exception:  # the library reports the malformed request
+        w, h = 640, 480
     out = np.empty((h, w, 4), np.uint8)
     wo, ho, st = C.c_uint32(), C.c_uint32(), RenderStats()
     _check(lib().ptb_worker_run(text.encode(), os.fsencode(scene_dir), device,
