@@ -44,6 +44,7 @@ CONFIGS = {
     "c1": ("C1 cornell-box 256x256 16spp depth4 LIB", 256, 256, 16, 4, 0),
     "c2": ("C2 heightfield 999698 tris 1920x1080 64spp depth4 LIB", 1920, 1080, 64, 4, 0),
     "c3": ("C3 cornell-box 1920x1080 256spp depth16 APP_RR", 1920, 1080, 256, 16, 1),
+    "c5": ("C5 49 instances x 999698-tri heightfield (49M instanced tris) 1920x1080 64spp depth4 LIB", 1920, 1080, 64, 4, 0),
 }
 
 
@@ -113,6 +114,8 @@ def build_description(cfg_name, n_grid):
     from ptb200 import procedural as P
     if cfg_name == "c2":
         return P.heightfield_scene(n_grid)
+    if cfg_name == "c5":
+        return P.instanced_heightfield_scene(n_grid, 7)
     return ptb.load_gltf_description(P.cornell_gltf_path())
 
 
