@@ -86,6 +86,7 @@ struct DSun {
 // Kernel argument (by value).
 struct DScene {
     const DInstance* instances;
+    const float4* inst_sphere; // conservative world-space bound per instance: centre xyz, radius (< 0: never hit)
     const DSurface* surfaces;
     const DMesh* meshes;
     const uint2* kd_nodes;

@@ -212,6 +212,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
 
         // ---- instances ----
         std::vector<DInstance> instances(desc.n_instances);
+        std::vector<float4> spheres(desc.n_instances);
         for (uint32_t i = 0; i < desc.n_instances; i++) {
             const ptb_instance_desc& id = desc.instances[i];
             DInstance& di = instances[i];
@@ -235,6 +236,36 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
             }
             di.first_surface = id.first_surface;
             di.n_surfaces = id.n_surfaces;
+            // Conservative world-space bounding sphere of the model box (double precision, 2 % + absolute slack):
+            // a regular ray that misses it misses the box in local space by far more than any rounding of the
+            // reference's slab test, so extend may skip the instance without changing a single result.
+            if (mn[0] > mx[0] || mn[1] > mx[1] || mn[2] > mx[2]) {
+                spheres[i] = make_float4(0, 0, 0, -1.0f); // aabb::intersect rejects min > max outright
+            } else {
+                double c[3], r2 = 0;
+                for (int a = 0; a < 3; a++) c[a] = 0.5 * (double(mn[a]) + double(mx[a]));
+                const M3& B = di.fwd.basis;
+                const double bx[3] = {B.x.x, B.x.y, B.x.z}, by[3] = {B.y.x, B.y.y, B.y.z}, bz[3] = {B.z.x, B.z.y, B.z.z};
+                double cw[3];
+                const double o3[3] = {di.fwd.origin.x, di.fwd.origin.y, di.fwd.origin.z};
+                for (int a = 0; a < 3; a++) cw[a] = bx[a] * c[0] + by[a] * c[1] + bz[a] * c[2] + o3[a];
+                for (int sx = -1; sx <= 1; sx += 2)
+                    for (int sy = -1; sy <= 1; sy += 2)
+                        for (int sz = -1; sz <= 1; sz += 2) {
+                            const double h[3] = {sx * 0.5 * (double(mx[0]) - mn[0]), sy * 0.5 * (double(mx[1]) - mn[1]),
+                                                 sz * 0.5 * (double(mx[2]) - mn[2])};
+                            double d2 = 0;
+                            for (int a = 0; a < 3; a++) {
+                                const double v = bx[a] * h[0] + by[a] * h[1] + bz[a] * h[2];
+                                d2 += v * v;
+                            }
+                            r2 = std::max(r2, d2);
+                        }
+                const double scale = std::sqrt(cw[0] * cw[0] + cw[1] * cw[1] + cw[2] * cw[2]) + std::sqrt(r2);
+                const double r = std::sqrt(r2) * 1.02 + 1e-3 * scale + 1e-4;
+                spheres[i] = make_float4(float(cw[0]), float(cw[1]), float(cw[2]),
+                                         std::isfinite(r) ? float(r) : 3.0e38f);
+            }
         }
         std::vector<DSurface> surfaces(desc.n_surfaces);
         for (uint32_t k = 0; k < desc.n_surfaces; k++) surfaces[k] = DSurface{desc.surfaces[k].mesh, desc.surfaces[k].material};
@@ -281,6 +312,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
         auto t1 = std::chrono::steady_clock::now();
         DScene& d = s->d;
         d.instances = upload(s, instances);
+        d.inst_sphere = upload(s, spheres);
         d.surfaces = upload(s, surfaces);
         d.meshes = upload(s, meshes);
         d.kd_nodes = upload(s, nodes);

@@ -161,6 +161,33 @@ def test_large_mesh_against_c_oracle(ptb, procedural, portlib, reflib):
     assert (want["instance"][16000:16010] == 0xFFFFFFFF).all()
 
 
+def test_many_instances_against_c_oracle(ptb, procedural, portlib, reflib):
+    """40 rotated / non-uniformly scaled instances of two meshes: the extend kernel skips instances through a
+    conservative world-space bound; every hit must still equal the reference algorithm's (no culling there)."""
+    rng = np.random.default_rng(9)
+    a, b = procedural.heightfield_mesh(6, 1.0, 3), procedural.heightfield_mesh(3, 0.7, 4)
+    insts = []
+    for i in range(40):
+        ang = rng.uniform(0, 6.28)
+        sc = rng.uniform(0.3, 1.8, 3)
+        c, s_ = np.cos(ang), np.sin(ang)
+        basis = np.array([c * sc[0], 0, -s_ * sc[0], 0, sc[1], 0, s_ * sc[2], 0, c * sc[2]], np.float32)
+        insts.append((rng.uniform(-8, 8, 3) * (1, 0.2, 1), basis, i % 2, 1))
+    mats = [dict(albedo=(0.7, 0.7, 0.7), roughness=1.0, metallic=0.0)] * 2
+    cam = procedural.look_at((0, 6, 14), (0, 0, 0))
+    args = ([a, b], [(0, 0), (1, 1)], insts, mats, (cam[0], cam[1], 0.8))
+    n = 300_000
+    o = (rng.uniform(-10, 10, (n, 3)) * (1, 0.4, 1)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:3000, 1] = 0  # irregular rays take the exact path (no culling)
+    od = np.concatenate([o, d], 1)
+    with ptb.Scene.create(ptb.SceneDescription(*args)) as s:
+        got = s.trace_rays(od)
+    want = portlib.PortScene(reflib.FlatScene(*args)).trace_rays(od)
+    H.assert_hits_equal(got, want, "40 instances vs C oracle")
+    assert 0.05 < (want["instance"] != 0xFFFFFFFF).mean() < 0.95
+
+
 def test_empty_and_tiny_inputs(cornell):
     assert len(cornell.trace_rays(np.zeros((0, 6), np.float32))) == 0
     one = cornell.trace_rays(np.array([[0, 2.3, 11.7, 0, 0, -1]], np.float32))
