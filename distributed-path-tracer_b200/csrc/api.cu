@@ -206,7 +206,7 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "count_visits") {
             ptb::g_options.count_visits = value ? 1 : 0;
         } else if (n == "extend_variant") {
-            if (value < 0 || value > 2) throw ptb::Error(PTB_E_INVALID, "extend_variant must be 0, 1 or 2");
+            if (value < 0 || value > 3) throw ptb::Error(PTB_E_INVALID, "extend_variant must be 0..3");
             ptb::g_options.extend_variant = value;
         } else if (n == "extend_steps") {
             if (value < 2 || value > 4) throw ptb::Error(PTB_E_INVALID, "extend_steps must be 2..4");
@@ -297,6 +297,7 @@ int ptb_device_count(void) {
     return n;
 }
 int ptb_extend_registers(void) {
+    if (ptb::g_options.extend_variant == 3) return ptb::extend_coop_regs_per_thread();
     return ptb::g_options.extend_variant == 0 ? ptb::extend_regs_per_thread() : ptb::extend_lanes_regs_per_thread();
 }
 uint64_t ptb_selftest_division(uint64_t n, uint64_t seed) { return ptb::division_selftest(n, seed); }

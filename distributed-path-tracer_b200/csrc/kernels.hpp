@@ -77,6 +77,11 @@ void launch_extend_lanes(const DScene& S, const float4* ray_o, const float4* ray
                          const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
                          cudaStream_t st);
 int extend_lanes_regs_per_thread();
+// extend_coop.cu — lane state machine + warp-cooperative leaf tests
+void launch_extend_coop(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
+                        const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
+                        cudaStream_t st);
+int extend_coop_regs_per_thread();
 unsigned long long division_selftest(uint64_t n, uint64_t seed);
 
 int extend_regs_per_thread();

@@ -89,6 +89,8 @@ void run_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4
                 const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg, cudaStream_t st) {
     if (cfg.extend_variant == 0)
         launch_extend(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
+    else if (cfg.extend_variant == 3)
+        launch_extend_coop(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
     else
         launch_extend_lanes(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
 }

@@ -30,7 +30,7 @@ def test_division_shortcut_is_exact(ptb):
     assert ptb.lib().ptb_selftest_division(1 << 28, 777) == 0
 
 
-@pytest.fixture(params=[1, 0], ids=["lanes", "simple"])
+@pytest.fixture(params=[3, 1, 0], ids=["coop", "lanes", "simple"])
 def extend_variant(ptb, request):
     ptb.set_option("extend_variant", request.param)
     yield request.param
