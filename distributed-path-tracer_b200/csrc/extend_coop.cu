@@ -306,10 +306,19 @@ __global__ void __launch_bounds__(C_THREADS, C_MIN_BLOCKS)
                                 V3{odx, ody, odz}, beta, gamma);
                 if (!(dist >= 0 && dist <= otmax)) dist = -1.0f; // "has_hit && distance <= max_dist"
             }
-            // segmented minimum per owner: nearest distance, lowest slot (= leaf order) on ties
-            const unsigned seg = __match_any_sync(0xFFFFFFFFu, active ? owner : -1 - (int)lane);
+            // segmented minimum per owner (segments are contiguous runs of slots): nearest distance; the ballot
+            // below then picks the lowest slot (= leaf order) among equal distances
             const uint32_t key = (dist >= 0) ? __float_as_uint(dist) : 0xFFFFFFFFu; // non-negative floats order as uints
-            const uint32_t seg_min = __reduce_min_sync(seg, key);
+            const int seg_id = active ? owner : -1 - (int)lane;
+            uint32_t red = key;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t other = __shfl_down_sync(0xFFFFFFFFu, red, off);
+                const int other_seg = __shfl_down_sync(0xFFFFFFFFu, seg_id, off);
+                if (lane + off < 32u && other_seg == seg_id) red = min(red, other);
+            }
+            // the first slot of a segment (slot opre of its owner) now holds the segment minimum
+            const uint32_t seg_min = __shfl_sync(0xFFFFFFFFu, red, active ? (int)opre : (int)lane);
             const unsigned winners = __ballot_sync(0xFFFFFFFFu, active && key != 0xFFFFFFFFu && key == seg_min);
             // back on the owner side: my slots are [pre, pre + take)
             const uint32_t take = (my_rem && pre < 32u) ? min(my_rem, 32u - pre) : 0u;
