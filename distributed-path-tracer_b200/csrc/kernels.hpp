@@ -49,6 +49,7 @@ struct LaunchCfg {
     bool count_visits;
     int extend_variant; // 0: one thread per ray (kernels.cu), 1: lane state machine (extend.cu)
     int extend_steps, extend_tests; // node steps / triangle tests offered per main-loop iteration (variant 1)
+    int extend_setup_lanes;         // waiting lanes that trigger the set-up section (variant 1)
 };
 
 // qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.

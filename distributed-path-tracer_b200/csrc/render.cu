@@ -104,6 +104,7 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.extend_variant = (int)g_options.extend_variant;
     c.extend_steps = (int)g_options.extend_steps;
     c.extend_tests = (int)g_options.extend_tests;
+    c.extend_setup_lanes = (int)g_options.extend_setup_lanes;
     return c;
 }
 

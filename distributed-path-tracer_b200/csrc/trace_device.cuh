@@ -59,12 +59,11 @@ struct KdStack {
 
 __device__ __forceinline__ float comp(V3 v, uint32_t axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
 
-// aabb::intersect + intersection::has_hit (far >= 0).
-__device__ __forceinline__ bool slab_test(const float* bmin, const float* bmax, V3 o, V3 d, float& near_out,
-                                          float& far_out) {
+// aabb::intersect + intersection::has_hit (far >= 0), given inv = 1 / d (componentwise, correctly rounded).
+__device__ __forceinline__ bool slab_test_inv(const float* bmin, const float* bmax, V3 o, V3 inv, float& near_out,
+                                              float& far_out) {
     if (bmin[0] > bmax[0] || bmin[1] > bmax[1] || bmin[2] > bmax[2])
         return false;
-    V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
     V3 t0 = (V3{bmin[0], bmin[1], bmin[2]} - o) * inv;
     V3 t1 = (V3{bmax[0], bmax[1], bmax[2]} - o) * inv;
     V3 nd = V3{rmin(t0.x, t1.x), rmin(t0.y, t1.y), rmin(t0.z, t1.z)};
@@ -76,6 +75,11 @@ __device__ __forceinline__ bool slab_test(const float* bmin, const float* bmax, 
     near_out = nr;
     far_out = fr;
     return fr >= 0;
+}
+
+__device__ __forceinline__ bool slab_test(const float* bmin, const float* bmax, V3 o, V3 d, float& near_out,
+                                          float& far_out) {
+    return slab_test_inv(bmin, bmax, o, V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z}, near_out, far_out);
 }
 
 // triangle::intersect.  Returns the distance, or -1 where the reference returns {-1}.

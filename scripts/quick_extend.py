@@ -1,4 +1,5 @@
-"""Quick extend timing on configs[1] geometry (time_stages); not a bench."""
+"""Quick extend timing on configs[1] geometry (time_stages); not a bench.
+usage: quick_extend.py [option=v1,v2,...]   e.g. extend_setup_lanes=4,8,12,16"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -6,9 +7,18 @@ import ptb200 as ptb
 from ptb200 import procedural as P
 s = ptb.Scene.create(P.heightfield_scene(707))
 ptb.set_option("time_stages", 1)
-best = None
-for rep in range(4):
-    rgb, a, st = s.render_tile(1920, 1080, 8, 4, seed=1)
-    if best is None or st["extend_seconds"] < best["extend_seconds"]:
-        best = st
-print(f"regs {ptb.lib().ptb_extend_registers()} extend {best['extend_seconds']*1e3:.2f} ms {best['rays']/best['extend_seconds']/1e6:.1f} Mrays/s total {best['gpu_seconds']*1e3:.2f} ms rays/path {best['rays']/best['paths']:.3f}")
+sweep = [(None, None)]
+if len(sys.argv) > 1:
+    name, vals = sys.argv[1].split("=")
+    sweep = [(name, int(v)) for v in vals.split(",")]
+for name, v in sweep:
+    if name:
+        ptb.set_option(name, v)
+    best = None
+    for rep in range(4):
+        rgb, a, st = s.render_tile(1920, 1080, 8, 4, seed=1)
+        if best is None or st["extend_seconds"] < best["extend_seconds"]:
+            best = st
+    print(f"{name}={v} regs {ptb.lib().ptb_extend_registers()} extend {best['extend_seconds']*1e3:.2f} ms "
+          f"{best['rays']/best['extend_seconds']/1e6:.1f} Mrays/s total {best['gpu_seconds']*1e3:.2f} ms "
+          f"rays/path {best['rays']/best['paths']:.3f}")
