@@ -48,7 +48,7 @@ struct DMesh {
     uint32_t tri_base;              // added to a reference to index tri_*
     uint32_t vtx_base;              // added to a vertex index
     uint32_t n_triangles;
-    uint32_t pad;
+    uint32_t pair_base;             // the mesh's root pair in kd_pairs (child pair indices are mesh-relative)
 };
 
 struct DMaterial {
@@ -90,6 +90,7 @@ struct DScene {
     const DSurface* surfaces;
     const DMesh* meshes;
     const uint2* kd_nodes;
+    const uint4* kd_pairs; // the same trees as sibling pairs (16 B: left record, right record), see scene.cu
     const uint32_t* kd_refs;
     const float4* tri; // 3 float4 per triangle: a, a-b, a-c (.w = the three vertex indices)
     const float* vtx_pos; // 3 per vertex

@@ -44,6 +44,52 @@ void require(bool ok, const char* msg) {
     if (!ok) throw Error(PTB_E_INVALID, msg);
 }
 
+// The traversal kernel's view of a tree: SIBLING PAIRS.  One 16-byte element holds the records of both
+// children of a branch (left in .xy, right in .zw), so a step fetches both with a single aligned load that
+// does not depend on the step's arithmetic, and the record of the far child can go onto the traversal
+// stack (a pop needs no further load).  A record is
+//   branch  x = split plane (float bits)      y = axis (0..2) | child pair index << 2   (mesh-relative)
+//   leaf    x = first reference               y = 3 | count << 2
+//   absent  x = 0                             y = 3           (the reference's null child, mesh.cpp:372)
+// Pair 0 of a mesh carries the root in .xy.  Same tree, same order of children: nothing about the
+// traversal's decisions changes.  Depth-first, left subtree first, so a descent to the left stays in a line.
+constexpr uint32_t KD_ABSENT_Y = KD_LEAF_TAG;
+
+void append_sibling_pairs(const KdTree& tree, std::vector<uint4>& pairs) {
+    const size_t base = pairs.size();
+    pairs.push_back(make_uint4(0, KD_ABSENT_Y, 0, KD_ABSENT_Y));
+    if (tree.nodes.empty()) return;
+    struct Item {
+        uint32_t src;  // index in tree.nodes
+        uint32_t pair; // destination pair (mesh-relative)
+        uint32_t half; // 0: .xy, 1: .zw
+    };
+    std::vector<Item> todo;
+    todo.push_back(Item{0, 0, 0});
+    while (!todo.empty()) {
+        const Item it = todo.back();
+        todo.pop_back();
+        const KdNode& n = tree.nodes[it.src];
+        uint32_t x = n.w0, y = n.w1;
+        if ((n.w1 & 3u) != KD_LEAF_TAG) {
+            const uint32_t has_l = (n.w1 >> 2) & 1u, has_r = (n.w1 >> 3) & 1u, first = n.w1 >> 4;
+            const uint32_t child_pair = static_cast<uint32_t>(pairs.size() - base);
+            pairs.push_back(make_uint4(0, KD_ABSENT_Y, 0, KD_ABSENT_Y));
+            y = (n.w1 & 3u) | (child_pair << 2);
+            if (has_r) todo.push_back(Item{first + has_l, child_pair, 1});
+            if (has_l) todo.push_back(Item{first, child_pair, 0}); // popped next: left subtree first
+        }
+        uint4& dst = pairs[base + it.pair];
+        if (it.half == 0) {
+            dst.x = x;
+            dst.y = y;
+        } else {
+            dst.z = x;
+            dst.w = y;
+        }
+    }
+}
+
 bool finite3(const float* p, size_t n) {
     for (size_t i = 0; i < n; i++)
         if (!std::isfinite(p[i])) return false;
@@ -158,6 +204,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
         auto t0 = std::chrono::steady_clock::now();
         std::vector<DMesh> meshes(desc.n_meshes);
         std::vector<uint2> nodes;
+        std::vector<uint4> pairs;
         std::vector<uint32_t> refs;
         std::vector<float4> tri;
         std::vector<float> vpos, vnrm, vtan, vuv;
@@ -180,8 +227,10 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
             dm.tri_base = static_cast<uint32_t>(tri.size() / 3);
             dm.vtx_base = static_cast<uint32_t>(vpos.size() / 3);
             dm.n_triangles = md.n_triangles;
-            dm.pad = 0;
+            dm.pair_base = static_cast<uint32_t>(pairs.size());
             for (const KdNode& n : tree.nodes) nodes.push_back(make_uint2(n.w0, n.w1));
+            append_sibling_pairs(tree, pairs);
+            require(pairs.size() < (1ull << 30), "KD sibling pairs exceed 30-bit indexing");
             refs.insert(refs.end(), tree.refs.begin(), tree.refs.end());
             for (uint32_t t = 0; t < md.n_triangles; t++) {
                 const uint32_t i0 = md.indices[3 * t], i1 = md.indices[3 * t + 1], i2 = md.indices[3 * t + 2];
@@ -316,6 +365,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
         d.surfaces = upload(s, surfaces);
         d.meshes = upload(s, meshes);
         d.kd_nodes = upload(s, nodes);
+        d.kd_pairs = upload(s, pairs);
         d.kd_refs = upload(s, refs);
         d.tri = upload(s, tri);
         d.vtx_pos = upload(s, vpos);
