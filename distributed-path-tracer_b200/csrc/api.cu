@@ -214,6 +214,8 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "extend_setup_lanes") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_setup_lanes must be 1..32");
             ptb::g_options.extend_setup_lanes = value;
+        } else if (n == "extend_sm_ranges") {
+            ptb::g_options.extend_sm_ranges = value != 0;
         } else if (n == "extend_tests") {
             if (value < 1 || value > 2) throw ptb::Error(PTB_E_INVALID, "extend_tests must be 1 or 2");
             ptb::g_options.extend_tests = value;

@@ -50,19 +50,35 @@ __device__ __forceinline__ KdStack make_stack(uint32_t* smem) {
     return s;
 }
 
-// Path p of the wave → sample s = p / padded_pixels, slot q = p % padded_pixels;
-// slots walk the tile in 8x4 pixel blocks so that a warp's primary rays form a
-// compact bundle.
+// Slots walk the tile in 8x4 pixel blocks (a warp's primary rays form a compact bundle), the blocks in
+// super-blocks of 8x8 (64x32 pixels), so that a stretch of the queue is a compact patch of the image and the
+// rays an SM works on at one time share nodes and triangles in its L1.
 __device__ __forceinline__ bool slot_to_pixel(const WaveGeom& g, uint32_t q, uint32_t& x, uint32_t& y) {
     const uint32_t blk = q >> 5, in = q & 31u;
-    const uint32_t bx = blk % g.blocks_x, by = blk / g.blocks_x;
+    const uint32_t sb = blk >> 6, inb = blk & 63u;
+    const uint32_t sby = sb / g.sblocks_x, sbx = sb - sby * g.sblocks_x;
+    const uint32_t bx = sbx * 8 + (inb & 7u), by = sby * 8 + (inb >> 3);
     x = bx * 8 + (in & 7u);
     y = by * 4 + (in >> 3);
     return x < g.w && y < g.h;
 }
 
 __device__ __forceinline__ uint32_t pixel_to_slot(const WaveGeom& g, uint32_t x, uint32_t y) {
-    return (((y >> 2) * g.blocks_x + (x >> 3)) << 5) + ((y & 3u) << 3) + (x & 7u);
+    const uint32_t bx = x >> 3, by = y >> 2;
+    const uint32_t sb = (by >> 3) * g.sblocks_x + (bx >> 3), inb = ((by & 7u) << 3) | (bx & 7u);
+    return (((sb << 6) | inb) << 5) + ((y & 3u) << 3) + (x & 7u);
+}
+
+// Path p of the wave ↔ (sample s of the wave, slot q): block-major, so the wave's samples of one 8x4 block
+// are adjacent in the queue (p = ((q / 32) * wave_samples + s) * 32 + q % 32).
+__device__ __forceinline__ void path_to_sample_slot(const WaveGeom& g, uint32_t p, uint32_t& s, uint32_t& q) {
+    const uint32_t bs = p >> 5, blk = bs / g.wave_samples;
+    s = bs - blk * g.wave_samples;
+    q = (blk << 5) | (p & 31u);
+}
+
+__device__ __forceinline__ size_t sample_slot_to_path(const WaveGeom& g, uint32_t s, uint32_t q) {
+    return ((size_t(q >> 5) * g.wave_samples + s) << 5) + (q & 31u);
 }
 
 // ------------------------------------------------------------- raygen ------
@@ -73,7 +89,8 @@ __global__ void __launch_bounds__(256)
     const uint32_t n = g.padded_pixels * g.wave_samples; // multiple of 32
     const int lane = threadIdx.x & 31;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const uint32_t s = p / g.padded_pixels, q = p - s * g.padded_pixels;
+        uint32_t s, q;
+        path_to_sample_slot(g, p, s, q);
         uint32_t x, y;
         const bool valid = slot_to_pixel(g, q, x, y);
         const unsigned mask = __ballot_sync(0xFFFFFFFFu, valid);
@@ -190,7 +207,8 @@ __device__ __forceinline__ bool shade_path(const DScene& S, const WaveGeom& g, c
     const MatSample m = material_sample(S, at.material, at.u, at.v);
 
     // random numbers of this shade event: a = (opacity, lobe, u1, u2), b = (sun phi, sun theta, roulette, -)
-    const uint32_t s = st.p / g.padded_pixels, q = st.p - s * g.padded_pixels;
+    uint32_t s, q;
+    path_to_sample_slot(g, st.p, s, q);
     uint32_t x, y;
     slot_to_pixel(g, q, x, y);
     const uint32_t pixel_id = (g.y0 + y) * g.full_w + (g.x0 + x);
@@ -376,7 +394,7 @@ __global__ void __launch_bounds__(256)
         float4 px = accum[i];
         bool cl = transparent ? (claimed[i] != 0) : false;
         for (uint32_t s = 0; s < g.wave_samples; s++) {
-            const float4 d = __ldcs(sample_out + size_t(s) * g.padded_pixels + q);
+            const float4 d = __ldcs(sample_out + sample_slot_to_path(g, s, q));
             const uint32_t sample = g.first_sample + s;
             if (transparent) {
                 if (d.w > 0.5 && !cl) {

@@ -19,7 +19,8 @@ struct WaveGeom {
     uint32_t full_w, full_h;       // frame resolution (camera aspect, ndc)
     uint32_t x0, y0, w, h;         // tile
     uint32_t blocks_x, blocks_y;   // tile in 8x4-pixel blocks
-    uint32_t padded_pixels;        // blocks_x * blocks_y * 32
+    uint32_t sblocks_x;            // tile width in super-blocks of 8x8 blocks (64x32 pixels)
+    uint32_t padded_pixels;        // slots: super-blocks * 64 * 32
     uint32_t wave_samples;         // samples of every pixel in this wave
     uint32_t first_sample;         // global index of the wave's first sample
 };
@@ -42,6 +43,8 @@ struct DeviceCounters {
     unsigned long long node_visits, leaf_visits, tri_tests, rays;
 };
 
+constexpr uint32_t QHEAD_STRIDE = 256; // work heads per extend launch: one per SM range (>= SM count)
+
 struct LaunchCfg {
     int sm_count;
     int extend_blocks_per_sm;
@@ -50,6 +53,7 @@ struct LaunchCfg {
     int extend_variant; // 0: one thread per ray (kernels.cu), 1: lane state machine (extend.cu)
     int extend_steps, extend_tests; // node steps / triangle tests offered per main-loop iteration (variant 1)
     int extend_setup_lanes;         // waiting lanes that trigger the set-up section (variant 1)
+    int extend_sm_ranges;           // 1: every SM works through its own contiguous part of the queue first
 };
 
 // qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.

@@ -105,6 +105,7 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.extend_steps = (int)g_options.extend_steps;
     c.extend_tests = (int)g_options.extend_tests;
     c.extend_setup_lanes = (int)g_options.extend_setup_lanes;
+    c.extend_sm_ranges = (int)g_options.extend_sm_ranges;
     return c;
 }
 
@@ -128,7 +129,8 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
     g.x0 = req.x0; g.y0 = req.y0; g.w = req.w; g.h = req.h;
     g.blocks_x = (req.w + 7) / 8;
     g.blocks_y = (req.h + 3) / 4;
-    const uint64_t padded = uint64_t(g.blocks_x) * g.blocks_y * 32;
+    g.sblocks_x = (g.blocks_x + 7) / 8;
+    const uint64_t padded = uint64_t(g.sblocks_x) * ((g.blocks_y + 7) / 8) * 64 * 32;
     if (padded >= (1ull << 31)) throw Error(PTB_E_INVALID, "tile too large");
     g.padded_pixels = (uint32_t)padded;
     uint64_t wave_samples = std::max<uint64_t>(1, (uint64_t)g_options.wave_paths / padded);
@@ -149,7 +151,7 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
     w.sample_out.ensure(cap * sizeof(float4));
     const uint32_t n_iters_fixed = req.max_depth;
     const size_t n_counters = size_t(n_iters_fixed) + MAX_EXTRA_ITERS + 2;
-    w.qcount.ensure(n_counters * 2 * sizeof(uint32_t));
+    w.qcount.ensure(n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t));
     w.counters.ensure(sizeof(DeviceCounters));
     const bool transparent = s->d.transparent_background != 0;
     if (transparent) w.claimed.ensure(size_t(req.w) * req.h);
@@ -187,7 +189,7 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
         g.wave_samples = (uint32_t)std::min<uint64_t>(wave_samples, req.spp - s0);
         g.first_sample = req.first_sample + s0;
         paths += uint64_t(req.w) * req.h * g.wave_samples;
-        PTB_CUDA(cudaMemsetAsync(qcount, 0, n_counters * 2 * sizeof(uint32_t), st));
+        PTB_CUDA(cudaMemsetAsync(qcount, 0, n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t), st));
         stage_begin(1);
         launch_raygen(s->d, g, rp, path_set(w, 0), (float4*)w.sample_out.p, &qcount[0], cfg, st);
         stage_end();
@@ -197,7 +199,8 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
         for (; it < n_iters_fixed; it++) {
             const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
             stage_begin(0);
-            run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg, st);
+            run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[size_t(it) * QHEAD_STRIDE],
+                       counters, cfg, st);
             stage_end();
             stage_begin(1);
             launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
@@ -215,8 +218,8 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
                 if (live == 0) break;
                 const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
                 stage_begin(0);
-                run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[it], counters, cfg,
-                              st);
+                run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it],
+                           &qhead[size_t(it) * QHEAD_STRIDE], counters, cfg, st);
                 stage_end();
                 stage_begin(1);
                 launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
@@ -297,10 +300,11 @@ void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, pt
     w.path[0][1].ensure(n * sizeof(float4));
     w.hits.ensure(n * sizeof(uint4));
     w.t.ensure(n * sizeof(float));
-    w.qcount.ensure(4 * sizeof(uint32_t));
+    w.qcount.ensure((1 + QHEAD_STRIDE) * sizeof(uint32_t));
     w.counters.ensure(sizeof(DeviceCounters));
     uint32_t* qc = (uint32_t*)w.qcount.p;
-    const uint32_t init[2] = {(uint32_t)n, 0u};
+    const uint32_t init[1] = {(uint32_t)n};
+    PTB_CUDA(cudaMemsetAsync(qc, 0, (1 + QHEAD_STRIDE) * sizeof(uint32_t), st));
     PTB_CUDA(cudaMemcpyAsync(qc, init, sizeof(init), cudaMemcpyHostToDevice, st));
     PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
     PTB_CUDA(cudaMemcpyAsync(w.io_a.p, origin_dir, n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));

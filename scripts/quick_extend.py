@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ptb200 as ptb
 from ptb200 import procedural as P
-s = ptb.Scene.create(P.heightfield_scene(707))
+s = ptb.Scene.create(P.heightfield_scene(int(os.environ.get('PTB_N', '707'))))
 ptb.set_option("time_stages", 1)
 sweep = [(None, None)]
 if len(sys.argv) > 1:
