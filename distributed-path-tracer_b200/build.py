@@ -23,7 +23,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OUT = os.path.join(HERE, "libptb.so")
 OBJ = os.path.join(HERE, "build")
 
-CU_SOURCES = ["kernels.cu", "extend.cu", "extend_coop.cu", "scene.cu", "render.cu", "api.cu"]
+CU_SOURCES = ["kernels.cu", "extend.cu", "extend_coop.cu", "extend_ctx.cu", "scene.cu", "render.cu", "api.cu"]
 CXX_SOURCES = ["kd_build.cpp", "gltf.cpp", "png.cpp"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

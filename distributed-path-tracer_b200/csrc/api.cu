@@ -1,6 +1,8 @@
 // api.cu — the extern "C" boundary declared in include/ptb.h.  Catches every
 // exception, maps it to a ptb_status and a thread-local message.
 
+#include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -206,7 +208,7 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "count_visits") {
             ptb::g_options.count_visits = value ? 1 : 0;
         } else if (n == "extend_variant") {
-            if (value < 0 || value > 3) throw ptb::Error(PTB_E_INVALID, "extend_variant must be 0..3");
+            if (value < 0 || value > 4) throw ptb::Error(PTB_E_INVALID, "extend_variant must be 0..4");
             ptb::g_options.extend_variant = value;
         } else if (n == "extend_steps") {
             if (value < 2 || value > 4) throw ptb::Error(PTB_E_INVALID, "extend_steps must be 2..4");
@@ -214,6 +216,9 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "extend_setup_lanes") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_setup_lanes must be 1..32");
             ptb::g_options.extend_setup_lanes = value;
+        } else if (n == "extend_contexts") {
+            if (value < 2 || value > 4) throw ptb::Error(PTB_E_INVALID, "extend_contexts must be 2..4");
+            ptb::g_options.extend_contexts = value;
         } else if (n == "extend_sm_ranges") {
             ptb::g_options.extend_sm_ranges = value != 0;
         } else if (n == "extend_tests") {
@@ -232,6 +237,30 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         }
     });
 }
+
+// PTB_OPTIONS="name=value,name=value": tuning options applied when the library is loaded (same names and
+// checks as ptb_set_option; a bad entry is reported on stderr and skipped).
+namespace {
+const int g_env_options_applied = [] {
+    const char* env = std::getenv("PTB_OPTIONS");
+    if (!env) return 0;
+    const std::string text(env);
+    size_t pos = 0;
+    while (pos < text.size()) {
+        size_t end = text.find(',', pos);
+        if (end == std::string::npos) end = text.size();
+        const std::string item = text.substr(pos, end - pos);
+        const size_t eq = item.find('=');
+        if (eq != std::string::npos) {
+            const std::string name = item.substr(0, eq);
+            if (ptb_set_option(name.c_str(), std::atoll(item.c_str() + eq + 1)) != PTB_OK)
+                std::fprintf(stderr, "libptb: PTB_OPTIONS entry '%s' rejected: %s\n", item.c_str(), ptb_last_error());
+        }
+        pos = end + 1;
+    }
+    return 1;
+}();
+} // namespace
 
 // The Lambda worker's entry (my_handler → worker::run, APP/main.cpp:9-31, APP/processors/worker/worker.cpp:25-105)
 // without the S3 hops: the request is the worker_info JSON the preprocessor sends, the scene is read from a local
@@ -303,6 +332,7 @@ int ptb_device_count(void) {
 }
 int ptb_extend_registers(void) {
     if (ptb::g_options.extend_variant == 3) return ptb::extend_coop_regs_per_thread();
+    if (ptb::g_options.extend_variant == 4) return ptb::extend_ctx_regs_per_thread((int)ptb::g_options.extend_contexts);
     return ptb::g_options.extend_variant == 0 ? ptb::extend_regs_per_thread() : ptb::extend_lanes_regs_per_thread();
 }
 uint64_t ptb_selftest_division(uint64_t n, uint64_t seed) { return ptb::division_selftest(n, seed); }

@@ -54,6 +54,7 @@ struct LaunchCfg {
     int extend_steps, extend_tests; // node steps / triangle tests offered per main-loop iteration (variant 1)
     int extend_setup_lanes;         // waiting lanes that trigger the set-up section (variant 1)
     int extend_sm_ranges;           // 1: every SM works through its own contiguous part of the queue first
+    int extend_contexts;            // rays per lane of the context kernel (variant 4): 2..4
 };
 
 // qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.
@@ -87,6 +88,11 @@ void launch_extend_coop(const DScene& S, const float4* ray_o, const float4* ray_
                         const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
                         cudaStream_t st);
 int extend_coop_regs_per_thread();
+// extend_ctx.cu — several ray contexts per lane, traversal state in shared memory
+void launch_extend_ctx(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
+                       const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
+                       cudaStream_t st);
+int extend_ctx_regs_per_thread(int contexts);
 unsigned long long division_selftest(uint64_t n, uint64_t seed);
 
 int extend_regs_per_thread();

@@ -91,6 +91,8 @@ void run_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4
         launch_extend(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
     else if (cfg.extend_variant == 3)
         launch_extend_coop(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
+    else if (cfg.extend_variant == 4)
+        launch_extend_ctx(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
     else
         launch_extend_lanes(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
 }
@@ -106,6 +108,7 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.extend_tests = (int)g_options.extend_tests;
     c.extend_setup_lanes = (int)g_options.extend_setup_lanes;
     c.extend_sm_ranges = (int)g_options.extend_sm_ranges;
+    c.extend_contexts = (int)g_options.extend_contexts;
     return c;
 }
 
