@@ -329,7 +329,7 @@ def run_ptb(args):
         nb, nl, nt = (sum(s[k] for s in st_c) for k in ("node_visits", "leaf_visits", "tri_tests"))
         alg_bytes = 32 * n_rays + 8 * nb + 8 * nl + (4 + 48) * nt + 32 * n_rays
         achieved = alg_bytes / ext_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "extend_kernel", "achieved": achieved, "peak": hbm_peak,
+        roofline = {"bound": "hbm", "kernel": "extend_lanes_kernel", "achieved": achieved, "peak": hbm_peak,
                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "bytes_per_ray": alg_bytes / max(n_rays, 1), "rays_per_launch": n_rays / max(ext_launches, 1),
                     "avg_launch_ms": ext_s / max(ext_launches, 1) * 1e3,
@@ -340,7 +340,10 @@ def run_ptb(args):
         prof = os.path.join(ROOT, "profiles", "extend_traffic.json")
         if os.path.exists(prof):
             try:
-                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                # measured DRAM bytes per ray of the ncu capture x the rays one launch processes here
+                tj = json.load(open(prof))
+                roofline["traffic"] = tj["dram_bytes_per_ray"] * roofline["rays_per_launch"]
+                roofline["traffic_source"] = "profiles/extend_traffic.json: dram bytes/ray under ncu x rays_per_launch"
             except Exception:
                 pass
 

@@ -72,12 +72,18 @@ __device__ __forceinline__ uint32_t pixel_to_slot(const WaveGeom& g, uint32_t x,
 // Path p of the wave ↔ (sample s of the wave, slot q): block-major, so the wave's samples of one 8x4 block
 // are adjacent in the queue (p = ((q / 32) * wave_samples + s) * 32 + q % 32).
 __device__ __forceinline__ void path_to_sample_slot(const WaveGeom& g, uint32_t p, uint32_t& s, uint32_t& q) {
+    if (!g.block_major) { // sample planes: p = s * padded_pixels + q
+        s = p / g.padded_pixels;
+        q = p - s * g.padded_pixels;
+        return;
+    }
     const uint32_t bs = p >> 5, blk = bs / g.wave_samples;
     s = bs - blk * g.wave_samples;
     q = (blk << 5) | (p & 31u);
 }
 
 __device__ __forceinline__ size_t sample_slot_to_path(const WaveGeom& g, uint32_t s, uint32_t q) {
+    if (!g.block_major) return size_t(s) * g.padded_pixels + q;
     return ((size_t(q >> 5) * g.wave_samples + s) << 5) + (q & 31u);
 }
 

@@ -23,6 +23,7 @@ struct WaveGeom {
     uint32_t padded_pixels;        // slots: super-blocks * 64 * 32
     uint32_t wave_samples;         // samples of every pixel in this wave
     uint32_t first_sample;         // global index of the wave's first sample
+    uint32_t block_major;          // path order: 1 = the wave's samples of an 8x4 block adjacent, 0 = sample planes
 };
 
 struct RenderParams {

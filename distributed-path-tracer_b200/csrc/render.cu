@@ -133,6 +133,7 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
     g.blocks_x = (req.w + 7) / 8;
     g.blocks_y = (req.h + 3) / 4;
     g.sblocks_x = (g.blocks_x + 7) / 8;
+    g.block_major = g_options.path_order != 0;
     const uint64_t padded = uint64_t(g.sblocks_x) * ((g.blocks_y + 7) / 8) * 64 * 32;
     if (padded >= (1ull << 31)) throw Error(PTB_E_INVALID, "tile too large");
     g.padded_pixels = (uint32_t)padded;
