@@ -224,3 +224,111 @@ def broadcast_description(desc, src: int = 0):
     return SceneDescription(meshes, np.array(meta["surfaces"], np.uint32).reshape(-1, 2), meta["instances"],
                             meta["materials"], meta["camera"], meta["sun"], meta["environment_factor"],
                             meta["transparent_background"], meta["kd_use_sah"], meta["kd_max_depth"], textures)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Geometry-sharded closest hit: the reference's own distribution axis.
+#
+# ``intersection_worker.cpp:69-147``: every worker holds a subset of the geometry, every ray visits every
+# worker, and the per-ray results are merged — closest hit = the smallest distance (``:85-92``), shadow ray =
+# OR of the workers' answers (``:126-133``).  Here a shard is a subset of the scene's INSTANCES (the unit
+# at which the reference's two-level model/mesh structure can be cut without touching a KD tree); meshes
+# that no kept instance uses are dropped from the shard, so a shard's HBM footprint is its own geometry only.
+#
+# The merge is exact: ``renderer::intersect`` scans the instances in order and keeps a candidate only when
+# it is strictly nearer (``renderer.cpp:663-669``), i.e. the result is the minimum of (distance, instance
+# index) in lexicographic order.  Distances of hits are non-negative floats, whose bit patterns order like
+# the numbers, so one integer MIN over the key  t_bits << 32 | instance << 12 | surface  reproduces the
+# unsharded answer bit for bit whatever the partition; the winner's triangle and barycentrics follow with
+# one SUM (exactly one rank owns the winning instance, everybody else contributes zeros).
+
+HIT_MISS_KEY = np.int64(0x7FFFFFFFFFFFFFFF)
+_SURFACE_BITS = 12  # kernels.hpp: HIT_SURFACE_BITS
+
+
+def shard_instances(desc, rank: int, world_size: int):
+    """→ (shard description, global instance index of every kept instance).  Instance i goes to rank
+    i % world_size; unused meshes / surfaces are dropped and the rest renumbered."""
+    from . import SceneDescription
+    keep = [i for i in range(len(desc.instances)) if i % world_size == rank]
+    surf_map, mesh_map, surfaces, meshes, instances = {}, {}, [], [], []
+    for i in keep:
+        o, b, first, count = desc.instances[i]
+        new_first = len(surfaces)
+        for s in range(first, first + count):
+            mesh, mat = (int(v) for v in desc.surfaces[s])
+            if mesh not in mesh_map:
+                mesh_map[mesh] = len(meshes)
+                meshes.append(desc.meshes[mesh])
+            surfaces.append((mesh_map[mesh], mat))
+            surf_map[s] = len(surfaces) - 1
+        instances.append((o, b, new_first, count))
+    shard = SceneDescription(meshes, np.array(surfaces, np.uint32).reshape(-1, 2), instances, desc.materials,
+                             desc.camera, desc.sun, desc.environment_factor, desc.transparent_background,
+                             desc.kd_use_sah, desc.kd_max_depth, desc.textures)
+    return shard, np.array(keep, np.uint32)
+
+
+def hit_keys(hits, instance_map) -> np.ndarray:
+    """Merge key per ray (int64): distance bits, then global instance, then surface; HIT_MISS_KEY for a miss."""
+    inst = hits["instance"]
+    miss = inst == np.uint32(0xFFFFFFFF)
+    glob = np.asarray(instance_map, np.uint32)[np.where(miss, 0, inst)] if len(instance_map) else inst
+    key = (hits["t"].view(np.uint32).astype(np.int64) << 32) | (glob.astype(np.int64) << _SURFACE_BITS) | \
+        hits["surface"].astype(np.int64)
+    return np.where(miss, HIT_MISS_KEY, key)
+
+
+def merge_closest_hits(hits, instance_map, device=None):
+    """All ranks pass their shard's hits for the SAME rays; every rank gets the merged hits (global instance
+    indices) — the closest-hit merge of ``intersection_worker.cpp:69-110`` as two all-reduces."""
+    from . import HIT_DTYPE
+    dist = _dist()
+    key = hit_keys(hits, instance_map)
+    payload = np.empty((len(hits), 4), np.int32)
+    payload[:, 0] = hits["triangle"].view(np.int32)
+    payload[:, 1:] = hits["bary"].view(np.int32)
+    best = key
+    if dist and dist.get_world_size() > 1:
+        import torch
+        tk = torch.from_numpy(key.copy())
+        tk = tk.to(device) if device is not None else tk
+        dist.all_reduce(tk, op=dist.ReduceOp.MIN)
+        best = tk.cpu().numpy()
+        mine = (key == best) & (best != HIT_MISS_KEY)
+        tp = torch.from_numpy(np.where(mine[:, None], payload, 0).astype(np.int32))
+        tp = tp.to(device) if device is not None else tp
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+        payload = tp.cpu().numpy()
+    return unpack_merged(best, payload, HIT_DTYPE)
+
+
+def unpack_merged(best_key, payload, hit_dtype):
+    """Merged keys + winner payload → hit records laid out like ptb_trace_rays' (misses: ids = 0xFFFFFFFF, t = -1)."""
+    out = np.zeros(len(best_key), hit_dtype)
+    miss = best_key == HIT_MISS_KEY
+    low = (best_key & 0xFFFFFFFF).astype(np.uint32)
+    out["instance"] = np.where(miss, np.uint32(0xFFFFFFFF), low >> np.uint32(_SURFACE_BITS))
+    out["surface"] = np.where(miss, np.uint32(0xFFFFFFFF), low & np.uint32((1 << _SURFACE_BITS) - 1))
+    out["t"] = np.where(miss, np.float32(-1.0), (best_key >> 32).astype(np.uint32).view(np.float32))
+    out["triangle"] = np.where(miss, np.uint32(0xFFFFFFFF), payload[:, 0].view(np.uint32))
+    out["bary"] = np.where(miss[:, None], np.float32(0), payload[:, 1:].view(np.float32))
+    return out
+
+
+def merge_occlusion(occluded, device=None):
+    """Shadow rays: a ray is occluded when ANY shard reports a hit (``intersection_worker.cpp:126-133``)."""
+    dist = _dist()
+    occ = np.ascontiguousarray(occluded, np.uint8)
+    if not dist or dist.get_world_size() == 1:
+        return occ.astype(bool)
+    import torch
+    t = torch.from_numpy(occ.copy())
+    t = t.to(device) if device is not None else t
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.cpu().numpy().astype(bool)
+
+
+def trace_rays_sharded(shard_scene, instance_map, origin_dir, device=None):
+    """Closest hits of `origin_dir` (identical on every rank) against the union of all ranks' shards."""
+    return merge_closest_hits(shard_scene.trace_rays(origin_dir), instance_map, device=device)

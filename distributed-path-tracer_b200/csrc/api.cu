@@ -117,7 +117,7 @@ ptb_status ptb_host_build_kd(const float* positions, uint32_t n_vertices, const 
             }
         }
         ptb::KdTree tree;
-        ptb::build_kd_tree(positions, indices, n_triangles, box, use_sah != 0, max_depth, threads, tree);
+        ptb::build_kd_tree_cached(positions, n_vertices, indices, n_triangles, box, use_sah != 0, max_depth, threads, tree);
         std::vector<uint32_t> w;
         ptb::dump_kd_tree(tree, w);
         *n_words = w.size();

@@ -37,7 +37,7 @@ enum : uint32_t { CS_FETCH = 0, CS_SETUP = 1, CS_DONE = 2, CS_TRAV = 3, CS_POP =
 enum : int {
     H_OX, H_OY, H_OZ, H_DX, H_DY, H_DZ, H_YX, H_YY, H_YZ, // ray in instance space, refined reciprocals of d
     H_TMIN, H_TMAX, H_NDX, H_NDY, H_SP, H_SLOW,           // segment, current record, stack height, exact-division flag
-    H_PAIRS, H_REFS, H_TRIS,                              // bases of the current mesh in kd_pairs / kd_refs / tri
+    H_TRIS,                                               // triangle base of the current mesh (pair / reference indices are absolute)
     H_LPOS, H_LEND, H_LT, H_LB, H_LG, H_LTRI,             // leaf cursor and the best hit in the current leaf
     H_COUNT
 };
@@ -232,8 +232,6 @@ __global__ void __launch_bounds__(T_THREADS, MINB)
                     float nr, fr;
                     if (slab_test_inv(M.aabb_min, M.aabb_max, o, inv, nr, fr)) {
                         const uint2 root = __ldg(reinterpret_cast<const uint2*>(S.kd_pairs + M.pair_base));
-                        HOT(H_PAIRS, kb) = M.pair_base;
-                        HOT(H_REFS, kb) = M.ref_base;
                         HOT(H_TRIS, kb) = M.tri_base;
                         HOT(H_NDX, kb) = root.x;
                         HOT(H_NDY, kb) = root.y;
@@ -278,7 +276,6 @@ __global__ void __launch_bounds__(T_THREADS, MINB)
                 uint2 nd = make_uint2(HOT(H_NDX, kb), HOT(H_NDY, kb));
                 int sp = (int)HOT(H_SP, kb);
                 const bool slowdiv = HOT(H_SLOW, kb) != 0;
-                const uint4* __restrict__ pairs = S.kd_pairs + HOT(H_PAIRS, kb);
                 uint4* const stack = stk + kt * KD_STACK_DEPTH;
 #pragma unroll
                 for (int s = 0; s < STEPS; s++) {
@@ -298,7 +295,7 @@ __global__ void __launch_bounds__(T_THREADS, MINB)
                     if (st == CS_TRAV && (nd.y & 3u) != 3u) {
                         if (COUNT) c_nodes++;
                         // both children in one aligned 16-byte load, in flight during the arithmetic below
-                        const uint4 ch = __ldg(pairs + (nd.y >> 2));
+                        const uint4 ch = __ldg(S.kd_pairs + (nd.y >> 2));
                         const uint32_t axis = nd.y & 3u;
                         const float split = __uint_as_float(nd.x);
                         float oa, da, ya;
@@ -360,7 +357,7 @@ __global__ void __launch_bounds__(T_THREADS, MINB)
                 const uint32_t lend = HOT(H_LEND, kb);
                 float lt = HOTF(H_LT, kb), lb = HOTF(H_LB, kb), lg = HOTF(H_LG, kb);
                 uint32_t ltri = HOT(H_LTRI, kb);
-                const uint32_t* __restrict__ refs = S.kd_refs + HOT(H_REFS, kb);
+                const uint32_t* __restrict__ refs = S.kd_refs;
                 const float4* __restrict__ tris = S.tri + size_t(HOT(H_TRIS, kb)) * 3;
                 // two triangles per visit, fetched together: two independent load → test chains
                 const bool two = lpos + 1 < lend;

@@ -3,6 +3,10 @@
 #include "kd_build.hpp"
 
 #include <algorithm>
+#include <functional>
+#include <string>
+#include <cstdlib>
+#include <cstdio>
 #include <atomic>
 #include <cfloat>
 #include <cstring>
@@ -357,6 +361,121 @@ void build_kd_tree(const float* positions, const uint32_t* indices, uint32_t n_t
 void dump_kd_tree(const KdTree& tree, std::vector<uint32_t>& words) {
     words.clear();
     if (!tree.nodes.empty()) dump_rec(tree, 0, words);
+}
+
+} // namespace ptb
+
+// ---- on-disk cache -------------------------------------------------------------------------------------
+
+namespace ptb {
+
+namespace {
+
+constexpr uint64_t KD_CACHE_MAGIC = 0x3130444B42545050ull; // "PPTBKD01"
+
+struct Hash2 {
+    uint64_t a = 0xcbf29ce484222325ull, b = 0x9E3779B97F4A7C15ull;
+    void feed(const void* data, size_t bytes) {
+        const unsigned char* p = static_cast<const unsigned char*>(data);
+        // a: FNV-1a over 8-byte words (tail bytewise); b: multiply-xorshift mix of the same words
+        size_t i = 0;
+        for (; i + 8 <= bytes; i += 8) {
+            uint64_t w;
+            std::memcpy(&w, p + i, 8);
+            a = (a ^ w) * 0x100000001b3ull;
+            b += w * 0xBF58476D1CE4E5B9ull;
+            b = (b ^ (b >> 29)) * 0x94D049BB133111EBull;
+        }
+        for (; i < bytes; i++) {
+            a = (a ^ p[i]) * 0x100000001b3ull;
+            b = (b ^ (uint64_t(p[i]) + 0x9E37u)) * 0x94D049BB133111EBull;
+        }
+    }
+    template <typename T>
+    void feed_value(const T& v) { feed(&v, sizeof(T)); }
+};
+
+struct CacheHeader {
+    uint64_t magic, key_a, key_b;
+    uint64_t n_nodes, n_refs, n_branches, n_leaves;
+    uint32_t max_depth_reached, reserved;
+};
+
+uint64_t payload_checksum(const KdTree& t) {
+    Hash2 h;
+    h.feed(t.nodes.data(), t.nodes.size() * sizeof(KdNode));
+    h.feed(t.refs.data(), t.refs.size() * sizeof(uint32_t));
+    return h.a ^ h.b;
+}
+
+bool load_tree(const std::string& path, uint64_t ka, uint64_t kb, KdTree& out) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    bool ok = false;
+    CacheHeader h{};
+    if (std::fread(&h, sizeof(h), 1, f) == 1 && h.magic == KD_CACHE_MAGIC && h.key_a == ka && h.key_b == kb &&
+        h.n_nodes < (1ull << 32) && h.n_refs < (1ull << 32)) {
+        KdTree t;
+        t.nodes.resize(h.n_nodes);
+        t.refs.resize(h.n_refs);
+        uint64_t sum = 0;
+        if (std::fread(t.nodes.data(), sizeof(KdNode), h.n_nodes, f) == h.n_nodes &&
+            std::fread(t.refs.data(), sizeof(uint32_t), h.n_refs, f) == h.n_refs &&
+            std::fread(&sum, sizeof(sum), 1, f) == 1 && sum == payload_checksum(t)) {
+            t.n_branches = h.n_branches;
+            t.n_leaves = h.n_leaves;
+            t.max_depth_reached = h.max_depth_reached;
+            out = std::move(t);
+            ok = true;
+        }
+    }
+    std::fclose(f);
+    return ok;
+}
+
+void store_tree(const std::string& path, uint64_t ka, uint64_t kb, const KdTree& t) {
+    const std::string tmp = path + ".tmp" + std::to_string((unsigned long long)std::hash<std::thread::id>()(std::this_thread::get_id()));
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return; // an unwritable cache directory is not an error: the tree is simply not cached
+    CacheHeader h{KD_CACHE_MAGIC, ka, kb, t.nodes.size(), t.refs.size(), t.n_branches, t.n_leaves, t.max_depth_reached, 0};
+    const uint64_t sum = payload_checksum(t);
+    const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 &&
+                    std::fwrite(t.nodes.data(), sizeof(KdNode), t.nodes.size(), f) == t.nodes.size() &&
+                    std::fwrite(t.refs.data(), sizeof(uint32_t), t.refs.size(), f) == t.refs.size() &&
+                    std::fwrite(&sum, sizeof(sum), 1, f) == 1;
+    const bool closed = std::fclose(f) == 0;
+    if (ok && closed)
+        std::rename(tmp.c_str(), path.c_str()); // atomic: readers see the old file, no file, or the whole new file
+    else
+        std::remove(tmp.c_str());
+}
+
+} // namespace
+
+bool build_kd_tree_cached(const float* positions, uint32_t n_vertices, const uint32_t* indices, uint32_t n_triangles,
+                          const Aabb& root, bool use_sah, uint32_t max_depth, int threads, KdTree& out) {
+    const char* dir = std::getenv("PTB_KD_CACHE");
+    if (!dir || !*dir) {
+        build_kd_tree(positions, indices, n_triangles, root, use_sah, max_depth, threads, out);
+        return false;
+    }
+    Hash2 h;
+    const uint32_t version = 1, sah = use_sah ? 1u : 0u;
+    h.feed_value(version);
+    h.feed_value(n_vertices);
+    h.feed_value(n_triangles);
+    h.feed_value(sah);
+    h.feed_value(max_depth);
+    h.feed(&root, sizeof(root));
+    h.feed(positions, size_t(n_vertices) * 3 * sizeof(float));
+    h.feed(indices, size_t(n_triangles) * 3 * sizeof(uint32_t));
+    char name[64];
+    std::snprintf(name, sizeof(name), "/kd_%016llx%016llx.bin", (unsigned long long)h.a, (unsigned long long)h.b);
+    const std::string path = std::string(dir) + name;
+    if (load_tree(path, h.a, h.b, out)) return true;
+    build_kd_tree(positions, indices, n_triangles, root, use_sah, max_depth, threads, out);
+    store_tree(path, h.a, h.b, out);
+    return false;
 }
 
 } // namespace ptb

@@ -50,6 +50,14 @@ Aabb mesh_aabb(const float* positions, uint32_t n_vertices);
 void build_kd_tree(const float* positions, const uint32_t* indices, uint32_t n_triangles, const Aabb& root,
                    bool use_sah, uint32_t max_depth, int threads, KdTree& out);
 
+// build_kd_tree behind an on-disk cache of the flattened tree.  The cache directory is the
+// environment variable PTB_KD_CACHE (unset or empty: no cache).  A file is named by two independent 64-bit
+// hashes of everything the tree depends on (vertex positions, indices, root box, builder kind, depth limit,
+// format version) and is verified on load (sizes, magic, trailing checksum); a damaged or foreign file is
+// ignored and rebuilt.  Returns true when the tree came from the cache.
+bool build_kd_tree_cached(const float* positions, uint32_t n_vertices, const uint32_t* indices, uint32_t n_triangles,
+                          const Aabb& root, bool use_sah, uint32_t max_depth, int threads, KdTree& out);
+
 // Depth-first record stream documented at ptb_scene_dump_kd (include/ptb.h).
 void dump_kd_tree(const KdTree& tree, std::vector<uint32_t>& words);
 

@@ -48,14 +48,15 @@ void require(bool ok, const char* msg) {
 // children of a branch (left in .xy, right in .zw), so a step fetches both with a single aligned load that
 // does not depend on the step's arithmetic, and the record of the far child can go onto the traversal
 // stack (a pop needs no further load).  A record is
-//   branch  x = split plane (float bits)      y = axis (0..2) | child pair index << 2   (mesh-relative)
-//   leaf    x = first reference               y = 3 | count << 2
+//   branch  x = split plane (float bits)      y = axis (0..2) | child pair index << 2   (index into kd_pairs)
+//   leaf    x = first reference (index into kd_refs)   y = 3 | count << 2
 //   absent  x = 0                             y = 3           (the reference's null child, mesh.cpp:372)
-// Pair 0 of a mesh carries the root in .xy.  Same tree, same order of children: nothing about the
+// Indices are ABSOLUTE (all meshes share the arrays), so the kernel carries no per-mesh base for them.
+// The first pair of a mesh (DMesh::pair_base) carries the root in .xy.  Same tree, same order of children: nothing about the
 // traversal's decisions changes.  Depth-first, left subtree first, so a descent to the left stays in a line.
 constexpr uint32_t KD_ABSENT_Y = KD_LEAF_TAG;
 
-void append_sibling_pairs(const KdTree& tree, std::vector<uint4>& pairs) {
+void append_sibling_pairs(const KdTree& tree, uint32_t ref_base, std::vector<uint4>& pairs) {
     const size_t base = pairs.size();
     pairs.push_back(make_uint4(0, KD_ABSENT_Y, 0, KD_ABSENT_Y));
     if (tree.nodes.empty()) return;
@@ -73,11 +74,14 @@ void append_sibling_pairs(const KdTree& tree, std::vector<uint4>& pairs) {
         uint32_t x = n.w0, y = n.w1;
         if ((n.w1 & 3u) != KD_LEAF_TAG) {
             const uint32_t has_l = (n.w1 >> 2) & 1u, has_r = (n.w1 >> 3) & 1u, first = n.w1 >> 4;
-            const uint32_t child_pair = static_cast<uint32_t>(pairs.size() - base);
+            const uint32_t child_pair = static_cast<uint32_t>(pairs.size());
             pairs.push_back(make_uint4(0, KD_ABSENT_Y, 0, KD_ABSENT_Y));
             y = (n.w1 & 3u) | (child_pair << 2);
-            if (has_r) todo.push_back(Item{first + has_l, child_pair, 1});
-            if (has_l) todo.push_back(Item{first, child_pair, 0}); // popped next: left subtree first
+            const uint32_t rel = child_pair - static_cast<uint32_t>(base);
+            if (has_r) todo.push_back(Item{first + has_l, rel, 1});
+            if (has_l) todo.push_back(Item{first, rel, 0}); // popped next: left subtree first
+        } else {
+            x = n.w0 + ref_base;
         }
         uint4& dst = pairs[base + it.pair];
         if (it.half == 0) {
@@ -213,7 +217,8 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
             const ptb_mesh_desc& md = desc.meshes[m];
             const Aabb box = mesh_aabb(md.positions, md.n_vertices);
             KdTree& tree = s->trees[m];
-            build_kd_tree(md.positions, md.indices, md.n_triangles, box, desc.kd_use_sah != 0, max_depth, 0, tree);
+            build_kd_tree_cached(md.positions, md.n_vertices, md.indices, md.n_triangles, box, desc.kd_use_sah != 0,
+                                 max_depth, 0, tree);
             require(nodes.size() + tree.nodes.size() < (1ull << 32), "KD nodes exceed 32-bit indexing");
             require(refs.size() + tree.refs.size() < (1ull << 32), "KD leaf references exceed 32-bit indexing");
             require(tri.size() / 3 + md.n_triangles < (1ull << 30), "triangles exceed 30-bit indexing");
@@ -229,7 +234,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
             dm.n_triangles = md.n_triangles;
             dm.pair_base = static_cast<uint32_t>(pairs.size());
             for (const KdNode& n : tree.nodes) nodes.push_back(make_uint2(n.w0, n.w1));
-            append_sibling_pairs(tree, pairs);
+            append_sibling_pairs(tree, dm.ref_base, pairs);
             require(pairs.size() < (1ull << 30), "KD sibling pairs exceed 30-bit indexing");
             refs.insert(refs.end(), tree.refs.begin(), tree.refs.end());
             for (uint32_t t = 0; t < md.n_triangles; t++) {

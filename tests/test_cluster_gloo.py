@@ -57,8 +57,60 @@ def _worker(rank, world, port, static, out_dir):
         for k in a:
             assert np.array_equal(a[k], b[k])
     assert got.instances[1][2:] == ref.instances[1][2:] and got.materials == ref.materials
+    _geometry_sharding(rank, world, cluster, procedural)
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
+
+
+def _instanced_scene(procedural, ptb_mod):
+    rng = np.random.default_rng(11)
+    a, b = procedural.heightfield_mesh(6, 1.0, 3), procedural.heightfield_mesh(3, 0.7, 4)
+    insts = []
+    for i in range(9):
+        ang = rng.uniform(0, 6.28)
+        sc = rng.uniform(0.5, 1.6, 3)
+        c, s_ = np.cos(ang), np.sin(ang)
+        basis = np.array([c * sc[0], 0, -s_ * sc[0], 0, sc[1], 0, s_ * sc[2], 0, c * sc[2]], np.float32)
+        insts.append((rng.uniform(-4, 4, 3) * (1, 0.2, 1), basis, i % 2, 1))
+    insts.append(((0, 0.1, 0), np.eye(3, dtype=np.float32).ravel(), 0, 2))  # two surfaces, overlaps instance 0..8
+    insts.append(insts[2])  # an exact duplicate: equal distances, the lower instance index must win
+    mats = [dict(albedo=(0.7, 0.7, 0.7), roughness=1.0, metallic=0.0)] * 2
+    cam = procedural.look_at((0, 6, 14), (0, 0, 0))
+    return ptb_mod.SceneDescription([a, b], [(0, 0), (1, 1)], insts, mats, (cam[0], cam[1], 0.8))
+
+
+def _geometry_sharding(rank, world, cluster, procedural):
+    """Closest-hit merge across geometry shards (intersection_worker.cpp:69-147) == the unsharded search, bit for
+    bit; the per-shard searches are done by the plain-C oracle (this is a CPU test)."""
+    import importlib
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import portlib
+    import reflib
+    ptb_mod = importlib.import_module("distributed-path-tracer_b200")
+    desc = _instanced_scene(procedural, ptb_mod)
+    rng = np.random.default_rng(3)
+    n = 20_000
+    o = (rng.uniform(-6, 6, (n, 3)) * (1, 0.4, 1)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    od = np.concatenate([o, d], 1)
+
+    def flat(ds):
+        return reflib.FlatScene(ds.meshes, ds.surfaces, ds.instances, ds.materials, ds.camera)
+
+    want = portlib.PortScene(flat(desc)).trace_rays(od)
+    shard, imap = cluster.shard_instances(desc, rank, world)
+    assert list(imap) == [i for i in range(len(desc.instances)) if i % world == rank]
+    local = portlib.PortScene(flat(shard)).trace_rays(od)
+    got = cluster.merge_closest_hits(local, imap)
+    for f in ("instance", "surface", "triangle"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    assert np.array_equal(got["bary"].view(np.uint32), want["bary"].view(np.uint32))
+    hit = want["instance"] != 0xFFFFFFFF
+    assert 0.02 < hit.mean() < 0.95 and (want["instance"][hit] == 9).any(), hit.mean()
+    assert not (want["instance"] == 10).any()  # the duplicate never wins a tie against instance 2
+    occ = cluster.merge_occlusion(local["instance"] != 0xFFFFFFFF)
+    assert np.array_equal(occ, hit)
 
 
 @pytest.mark.parametrize("static", [False, True])

@@ -30,17 +30,54 @@ def test_division_shortcut_is_exact(ptb):
     assert ptb.lib().ptb_selftest_division(1 << 28, 777) == 0
 
 
-@pytest.fixture(params=[3, 1, 0], ids=["coop", "lanes", "simple"])
+VARIANTS = {"simple": (0, 2), "lanes": (1, 2), "lanes-prefetch": (2, 2), "coop": (3, 2), "ctx2": (4, 2), "ctx3": (4, 3),
+            "ctx4": (4, 4)}
+
+
+@pytest.fixture(params=list(VARIANTS), ids=list(VARIANTS))
 def extend_variant(ptb, request):
-    ptb.set_option("extend_variant", request.param)
+    """Every extend kernel the library carries (extend_variant / extend_contexts), default restored afterwards."""
+    variant, contexts = VARIANTS[request.param]
+    ptb.set_option("extend_variant", variant)
+    ptb.set_option("extend_contexts", contexts)
     yield request.param
     ptb.set_option("extend_variant", 1)
+    ptb.set_option("extend_contexts", 2)
 
 
-def test_both_extend_kernels_against_goldens(cornell, extend_variant):
+def test_every_extend_kernel_against_goldens(cornell, extend_variant):
     r = H.load("cornell_rays.npz")
     for key in ("cam", "rnd", "bounce"):
         H.assert_hits_equal(cornell.trace_rays(r[key + "_rays"]), r[key + "_hits"], f"variant {extend_variant}:{key}")
+
+
+def test_every_extend_kernel_on_instances_and_a_deep_tree(ptb, procedural, extend_variant):
+    """Multi-surface / multi-instance set-up logic and a 20 000-triangle tree (deep stacks, long leaves): every
+    kernel must return, bit for bit, what the default one returns (which the other tests pin to the oracle)."""
+    rng = np.random.default_rng(5)
+    a, b = procedural.heightfield_mesh(100, 1.0, 3), procedural.heightfield_mesh(5, 0.7, 4)
+    insts = []
+    for i in range(12):
+        ang = rng.uniform(0, 6.28)
+        sc = rng.uniform(0.4, 1.5, 3)
+        c, s_ = np.cos(ang), np.sin(ang)
+        basis = np.array([c * sc[0], 0, -s_ * sc[0], 0, sc[1], 0, s_ * sc[2], 0, c * sc[2]], np.float32)
+        insts.append((rng.uniform(-6, 6, 3) * (1, 0.2, 1), basis, 0 if i % 3 else 1, 1))
+    insts.append(((0, 0, 0), np.eye(3, dtype=np.float32).ravel(), 0, 2))  # one instance with two surfaces
+    mats = [dict(albedo=(0.7, 0.7, 0.7), roughness=1.0, metallic=0.0)] * 2
+    cam = procedural.look_at((0, 6, 14), (0, 0, 0))
+    desc = ptb.SceneDescription([a, b], [(0, 0), (1, 1)], insts, mats, (cam[0], cam[1], 0.8))
+    n = 200_000
+    o = (rng.uniform(-9, 9, (n, 3)) * (1, 0.4, 1)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:2000, 2] = 0
+    od = np.concatenate([o, d], 1)
+    with ptb.Scene.create(desc) as s:
+        got = s.trace_rays(od)
+        ptb.set_option("extend_variant", 1)
+        want = s.trace_rays(od)
+    H.assert_hits_equal(got, want, f"variant {extend_variant} vs default")
+    assert 0.05 < (want["instance"] != 0xFFFFFFFF).mean() < 0.98
 
 
 def test_scene_trees_on_device_match_reference(cornell):
@@ -186,6 +223,52 @@ def test_many_instances_against_c_oracle(ptb, procedural, portlib, reflib):
     want = portlib.PortScene(reflib.FlatScene(*args)).trace_rays(od)
     H.assert_hits_equal(got, want, "40 instances vs C oracle")
     assert 0.05 < (want["instance"] != 0xFFFFFFFF).mean() < 0.95
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_geometry_shards_merge_to_the_unsharded_answer(ptb, procedural, world):
+    """SURVEY §8f-4 / intersection_worker.cpp:69-110 on the GPU kernel's output: the scene cut into `world`
+    instance shards (each its own device scene, only its own meshes resident), every shard traced with the same
+    rays, keys merged with the integer MIN the all-reduce uses — must equal the unsharded search bit for bit
+    (incl. ties between overlapping duplicates and misses)."""
+    import importlib
+    cluster = importlib.import_module("distributed-path-tracer_b200.cluster")
+    rng = np.random.default_rng(21)
+    a, b = procedural.heightfield_mesh(30, 1.0, 3), procedural.heightfield_mesh(4, 0.7, 4)
+    insts = []
+    for i in range(21):
+        ang = rng.uniform(0, 6.28)
+        sc = rng.uniform(0.4, 1.6, 3)
+        c, s_ = np.cos(ang), np.sin(ang)
+        basis = np.array([c * sc[0], 0, -s_ * sc[0], 0, sc[1], 0, s_ * sc[2], 0, c * sc[2]], np.float32)
+        insts.append((rng.uniform(-5, 5, 3) * (1, 0.2, 1), basis, i % 2, 1))
+    insts.append(((0, 0.1, 0), np.eye(3, dtype=np.float32).ravel(), 0, 2))
+    insts.append(insts[4])  # exact duplicate of instance 4 (another shard for every world here): ties
+    mats = [dict(albedo=(0.7, 0.7, 0.7), roughness=1.0, metallic=0.0)] * 2
+    cam = procedural.look_at((0, 6, 14), (0, 0, 0))
+    desc = ptb.SceneDescription([a, b], [(0, 0), (1, 1)], insts, mats, (cam[0], cam[1], 0.8))
+    n = 150_000
+    o = (rng.uniform(-7, 7, (n, 3)) * (1, 0.4, 1)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    od = np.concatenate([o, d], 1)
+    with ptb.Scene.create(desc) as s:
+        want = s.trace_rays(od)
+    best = np.full(n, cluster.HIT_MISS_KEY, np.int64)
+    payload = np.zeros((n, 4), np.int32)
+    for rank in range(world):
+        shard, imap = cluster.shard_instances(desc, rank, world)
+        with ptb.Scene.create(shard) as s:
+            assert s.info()["n_instances"] == len(imap)
+            local = s.trace_rays(od)
+        key = cluster.hit_keys(local, imap)
+        win = key < best
+        best = np.where(win, key, best)
+        payload[win, 0] = local["triangle"][win].view(np.int32)
+        payload[win, 1:] = local["bary"][win].view(np.int32)
+    got = cluster.unpack_merged(best, payload, ptb.HIT_DTYPE)
+    H.assert_hits_equal(got, want, f"{world} geometry shards")
+    assert np.array_equal(got["t"] >= 0, want["instance"] != 0xFFFFFFFF)
+    assert not (want["instance"] == 22).any() and (want["instance"] == 4).any()
 
 
 def test_empty_and_tiny_inputs(cornell):

@@ -65,6 +65,37 @@ def test_kd_builder_heightfield_any_thread_count(ptb, procedural, threads):
     assert np.array_equal(words, H.load("heightfield40_kd.npz")["mesh0"])
 
 
+def test_kd_tree_disk_cache(ptb, procedural, tmp_path, monkeypatch):
+    """PTB_KD_CACHE: the second build of the same mesh comes from disk and is the same tree; another mesh, another
+    depth limit or a damaged file never is."""
+    monkeypatch.setenv("PTB_KD_CACHE", str(tmp_path))
+    want = H.load("heightfield40_kd.npz")["mesh0"]
+    m = procedural.heightfield_mesh(40)
+    first, _ = ptb.host_build_kd(m["positions"], m["indices"])
+    files = sorted(tmp_path.glob("kd_*.bin"))
+    assert len(files) == 1 and np.array_equal(first, want)
+    stamp = files[0].stat().st_mtime_ns
+    again, _ = ptb.host_build_kd(m["positions"], m["indices"])
+    assert np.array_equal(again, want) and files[0].stat().st_mtime_ns == stamp  # served, not rewritten
+    # a different depth limit and a different mesh get their own entries
+    shallow, _ = ptb.host_build_kd(m["positions"], m["indices"], max_depth=6)
+    moved = m["positions"].copy()
+    moved[0, 1] += 0.25
+    other, _ = ptb.host_build_kd(moved, m["indices"])
+    assert len(list(tmp_path.glob("kd_*.bin"))) == 3
+    assert not np.array_equal(shallow, want) and not np.array_equal(other, want)
+    # a damaged file is ignored and replaced
+    raw = bytearray(files[0].read_bytes())
+    raw[len(raw) // 2] ^= 0xFF
+    files[0].write_bytes(bytes(raw))
+    healed, _ = ptb.host_build_kd(m["positions"], m["indices"])
+    assert np.array_equal(healed, want)
+    assert files[0].read_bytes() != bytes(raw)
+    monkeypatch.setenv("PTB_KD_CACHE", str(tmp_path / "does" / "not" / "exist"))
+    nocache, _ = ptb.host_build_kd(m["positions"], m["indices"])  # unwritable directory: builds, does not fail
+    assert np.array_equal(nocache, want)
+
+
 def test_kd_builder_against_c_oracle_on_awkward_meshes(ptb, portlib, reflib):
     """Degenerate / axis-aligned / duplicated / all-negative geometry: ties in the SAH sweep, the
     FLT_MIN quirk of aabb::clear, empty children."""
