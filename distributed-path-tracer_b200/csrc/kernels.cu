@@ -539,7 +539,11 @@ void launch_extend(const DScene& S, const float4* ray_o, const float4* ray_d, ui
                    const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
                    cudaStream_t st) {
     const size_t smem = STACK_SMEM_BYTES * EXT_THREADS;
-    const int grid = cfg.sm_count * cfg.extend_blocks_per_sm;
+    int per_sm = 0; // persistent grid: no more blocks than are resident at once
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel<false>, EXT_THREADS, smem) != cudaSuccess ||
+        per_sm <= 0)
+        per_sm = 4;
+    const int grid = cfg.sm_count * (per_sm < cfg.extend_blocks_per_sm ? per_sm : cfg.extend_blocks_per_sm);
     if (cfg.count_visits)
         extend_kernel<true><<<grid, EXT_THREADS, smem, st>>>(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters);
     else
