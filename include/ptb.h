@@ -322,12 +322,24 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
 
 /* ----------------------------------------------------------------- misc -- */
 
-/* Options: "wave_paths" (paths per wavefront), "count_visits" (0/1: instrumented
- * extend kernel), "time_stages" (0/1: CUDA events around every extend / shade
- * launch, filling extend_seconds / shade_seconds), "extend_variant" (1: lane
- * state machine with ray replacement, default; 0: the first one-thread-per-ray
- * kernel, kept for A/B checks), "extend_blocks_per_sm", "shade_blocks_per_sm".
- * Unknown names → PTB_E_INVALID. */
+/* Tuning options (none changes a result bit; all are for A/B measurements):
+ *   "wave_paths"            paths per wavefront (default 8 Mi)
+ *   "count_visits"          0/1: instrumented extend kernel (node / leaf / triangle visit counters)
+ *   "time_stages"           0/1: CUDA events around every extend / shade launch (extend_seconds, shade_seconds)
+ *   "extend_variant"        1: lane state machine with ray replacement (default); 0: first one-thread-per-ray
+ *                           kernel; 2: as 1 + L1 prefetch of the next triangle; 3: warp-cooperative leaf
+ *                           tests; 4: several ray contexts per lane, traversal state in shared memory
+ *   "extend_contexts"       rays per lane of variant 4 (2..4)
+ *   "extend_steps", "extend_tests"   node steps (2..4) / triangle tests (1..2) offered per loop iteration
+ *   "extend_setup_lanes"    waiting lanes that trigger the set-up section (1..32, default 8)
+ *   "extend_sm_ranges"      0/1: every SM starts on its own contiguous range of the ray queue (default 0)
+ *   "path_order"            1: a wave's samples of one 8x4 pixel block are adjacent in the queue (default);
+ *                           0: sample planes
+ *   "extend_blocks_per_sm", "shade_blocks_per_sm"   caps on the persistent grids
+ * Unknown names or out-of-range values → PTB_E_INVALID.
+ * Environment: PTB_OPTIONS="name=value,name=value" applies options when the library is loaded;
+ * PTB_KD_CACHE=<directory> caches flattened KD trees on disk (keyed by a hash of everything a tree depends
+ * on, checksummed; a damaged or foreign file is ignored and rebuilt). */
 ptb_status ptb_set_option(const char* name, int64_t value);
 
 const char* ptb_last_error(void);
