@@ -208,7 +208,7 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "count_visits") {
             ptb::g_options.count_visits = value ? 1 : 0;
         } else if (n == "extend_variant") {
-            if (value < 0 || value > 4) throw ptb::Error(PTB_E_INVALID, "extend_variant must be 0..4");
+            if (value < 0 || value > 4 || value == 2) throw ptb::Error(PTB_E_INVALID, "extend_variant must be 0, 1, 3 or 4");
             ptb::g_options.extend_variant = value;
         } else if (n == "extend_steps") {
             if (value < 2 || value > 4) throw ptb::Error(PTB_E_INVALID, "extend_steps must be 2..4");

@@ -327,8 +327,8 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
  *   "count_visits"          0/1: instrumented extend kernel (node / leaf / triangle visit counters)
  *   "time_stages"           0/1: CUDA events around every extend / shade launch (extend_seconds, shade_seconds)
  *   "extend_variant"        1: lane state machine with ray replacement (default); 0: first one-thread-per-ray
- *                           kernel; 2: as 1 + L1 prefetch of the next triangle; 3: warp-cooperative leaf
- *                           tests; 4: several ray contexts per lane, traversal state in shared memory
+ *                           kernel; 3: warp-cooperative leaf tests; 4: several ray contexts per lane,
+ *                           traversal state in shared memory (2 was an L1-prefetch experiment, removed)
  *   "extend_contexts"       rays per lane of variant 4 (2..4)
  *   "extend_steps", "extend_tests"   node steps (2..4) / triangle tests (1..2) offered per loop iteration
  *   "extend_setup_lanes"    waiting lanes that trigger the set-up section (1..32, default 8)

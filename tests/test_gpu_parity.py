@@ -30,7 +30,7 @@ def test_division_shortcut_is_exact(ptb):
     assert ptb.lib().ptb_selftest_division(1 << 28, 777) == 0
 
 
-VARIANTS = {"simple": (0, 2), "lanes": (1, 2), "lanes-prefetch": (2, 2), "coop": (3, 2), "ctx2": (4, 2), "ctx3": (4, 3),
+VARIANTS = {"simple": (0, 2), "lanes": (1, 2), "coop": (3, 2), "ctx2": (4, 2), "ctx3": (4, 3),
             "ctx4": (4, 4)}
 
 
