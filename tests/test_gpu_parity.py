@@ -210,6 +210,10 @@ def test_many_instances_against_c_oracle(ptb, procedural, portlib, reflib):
         c, s_ = np.cos(ang), np.sin(ang)
         basis = np.array([c * sc[0], 0, -s_ * sc[0], 0, sc[1], 0, s_ * sc[2], 0, c * sc[2]], np.float32)
         insts.append((rng.uniform(-8, 8, 3) * (1, 0.2, 1), basis, i % 2, 1))
+    # exact duplicates: equal distances — the reference's scan keeps the FIRST in scene order; the kernel walks the
+    # instances in its own (Morton) order and must break the tie by scene index
+    insts.append(insts[3])
+    insts.insert(0, insts[17])
     mats = [dict(albedo=(0.7, 0.7, 0.7), roughness=1.0, metallic=0.0)] * 2
     cam = procedural.look_at((0, 6, 14), (0, 0, 0))
     args = ([a, b], [(0, 0), (1, 1)], insts, mats, (cam[0], cam[1], 0.8))
@@ -221,8 +225,9 @@ def test_many_instances_against_c_oracle(ptb, procedural, portlib, reflib):
     with ptb.Scene.create(ptb.SceneDescription(*args)) as s:
         got = s.trace_rays(od)
     want = portlib.PortScene(reflib.FlatScene(*args)).trace_rays(od)
-    H.assert_hits_equal(got, want, "40 instances vs C oracle")
+    H.assert_hits_equal(got, want, "42 instances vs C oracle")
     assert 0.05 < (want["instance"] != 0xFFFFFFFF).mean() < 0.95
+    assert (want["instance"] == 0).any() and not (want["instance"] == 18).any() and not (want["instance"] == 41).any()
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
