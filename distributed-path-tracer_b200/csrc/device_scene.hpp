@@ -34,6 +34,7 @@ struct DInstance {
     M3 normal_mat; // transpose(inverse(fwd.basis)), LIB/core/renderer.cpp:698
     float aabb_min[3], aabb_max[3]; // scene::model::aabb (local space)
     uint32_t first_surface, n_surfaces;
+    uint32_t same_box; // 1: a single surface whose mesh box is bit for bit the model box (its slab test need not be repeated)
 };
 
 struct DSurface {

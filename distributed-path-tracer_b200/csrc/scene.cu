@@ -290,6 +290,12 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
             }
             di.first_surface = id.first_surface;
             di.n_surfaces = id.n_surfaces;
+            di.same_box = 0;
+            if (id.n_surfaces == 1) {
+                const DMesh& only = meshes[desc.surfaces[id.first_surface].mesh];
+                di.same_box = std::memcmp(only.aabb_min, di.aabb_min, sizeof(di.aabb_min)) == 0 &&
+                              std::memcmp(only.aabb_max, di.aabb_max, sizeof(di.aabb_max)) == 0;
+            }
             // Conservative world-space bounding sphere of the model box (double precision, 2 % + absolute slack):
             // a regular ray that misses it misses the box in local space by far more than any rounding of the
             // reference's slab test, so extend may skip the instance without changing a single result.
