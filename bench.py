@@ -9,7 +9,7 @@ on the named configuration; 1080p@64spp frames/s is reported inside `config`.
 A "step" is one pass of the hot path over one frame of synthetic input:
   * N = 1: configs[1] of BASELINE.json — the synthetic 999 698-triangle procedural heightfield,
     1920x1080, 64 spp, depth 4 (reference library default), integrator = renderer::trace semantics;
-  * N > 1 (torchrun, one rank per GPU): the same frame at 64*N spp, cut into 8*N tiles that the ranks
+  * N > 1 (torchrun, one rank per GPU): the same frame at 64*N spp, cut into 32*N tiles that the ranks
     claim from a shared counter (work stealing); per-GPU work is therefore fixed → "scaling": "weak".
     The render has no collective; the framebuffer gather (reduce of disjoint tiles onto rank 0 over
     NCCL) belongs to the end-to-end figure only.
@@ -399,7 +399,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--n-grid", type=int, default=707, help="heightfield grid (707 → 999 698 triangles)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
-    ap.add_argument("--tiles-per-gpu", type=int, default=8)
+    ap.add_argument("--tiles-per-gpu", type=int, default=32,
+                    help="tiles per GPU (work-stolen); more tiles = a shorter tail when ranks finish unevenly")
     ap.add_argument("--wave-paths", type=int, default=8 << 20)
     ap.add_argument("--streams", type=int, default=4, help="tiles in flight per GPU (host threads / CUDA streams)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference sample")
