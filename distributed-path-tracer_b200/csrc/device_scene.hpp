@@ -102,6 +102,7 @@ struct DScene {
     const DTexture* textures;
     const unsigned char* texels;
     uint32_t n_instances;
+    uint32_t n_pairs, n_refs, n_tris; // array sizes, for the instrumented kernel's bounds checks
     DCamera camera;
     DSun sun;
     V3 environment;

@@ -42,6 +42,7 @@ struct PathBuffers { // one of the two ping-pong sets, each array `capacity` flo
 
 struct DeviceCounters {
     unsigned long long node_visits, leaf_visits, tri_tests, rays;
+    unsigned long long bound_errors; // instrumented kernel only (count_visits): indices / stack heights out of range
 };
 
 constexpr uint32_t QHEAD_STRIDE = 256; // work heads per extend launch: one per SM range (>= SM count)

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "errors.hpp"
@@ -246,6 +247,9 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
         DeviceCounters hc{};
         PTB_CUDA(cudaMemcpyAsync(&hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
         PTB_CUDA(cudaStreamSynchronize(st));
+        if (hc.bound_errors)
+            throw Error(PTB_E_CUDA, "instrumented extend kernel: " + std::to_string(hc.bound_errors) +
+                                        " index / stack bound violations");
         float ms = 0;
         PTB_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1]));
         std::memset(stats, 0, sizeof(*stats));
@@ -325,6 +329,9 @@ void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, pt
     PTB_CUDA(cudaMemcpyAsync(&hc, w.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     PTB_CUDA(cudaStreamSynchronize(st));
     PTB_CUDA(cudaGetLastError());
+    if (hc.bound_errors)
+        throw Error(PTB_E_CUDA, "instrumented extend kernel: " + std::to_string(hc.bound_errors) +
+                                    " index / stack bound violations");
     if (stats) {
         float ms = 0;
         PTB_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1]));

@@ -387,6 +387,9 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
         d.textures = upload(s, textures);
         d.texels = upload(s, texels);
         d.n_instances = desc.n_instances;
+        d.n_pairs = static_cast<uint32_t>(pairs.size());
+        d.n_refs = static_cast<uint32_t>(refs.size());
+        d.n_tris = static_cast<uint32_t>(tri.size() / 3);
         d.camera.xf = xform_from(desc.camera.origin, desc.camera.basis);
         d.camera.tan_half_fov = std::tan(desc.camera.yfov * 0.5F); // camera::set_fov (glibc tanf, as the reference)
         d.sun.enabled = desc.sun.enabled ? 1 : 0;

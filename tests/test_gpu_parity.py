@@ -276,6 +276,35 @@ def test_geometry_shards_merge_to_the_unsharded_answer(ptb, procedural, world):
     assert not (want["instance"] == 22).any() and (want["instance"] == 4).any()
 
 
+def test_instrumented_kernel_finds_no_bound_violation(ptb, procedural, cornell):
+    """compute-sanitizer is not available on the GPU pool, so the instrumented build of the extend kernel
+    (count_visits) checks every pair / reference / triangle index and the traversal-stack height itself and the
+    call fails when one is out of range.  Deep tree with edge-case rays, the bundled scene, and a full render."""
+    rng = np.random.default_rng(77)
+    n = 300_000
+    o = (rng.uniform(-6, 6, (n, 3)) * (1, 0.25, 1) + (0, 1.0, 0)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:4000, 0] = 0
+    d[4000:8000] = (0, -1, 0)
+    o[8000:9000] *= np.float32(1e6)
+    d[9000:9010] = 0
+    d[9010:9020] = np.float32(np.inf)
+    od = np.concatenate([o, d], 1)
+    ptb.set_option("count_visits", 1)
+    try:
+        with ptb.Scene.create(procedural.heightfield_scene(250)) as s:
+            _, st = s.trace_rays(od, stats=True)
+            assert st["rays"] == n and st["node_visits"] > 10 * n
+            _, _, st2 = s.render_tile(320, 180, 4, 6, seed=3)
+            assert st2["tri_tests"] > 0
+        r = H.load("cornell_rays.npz")
+        for key in ("cam", "rnd", "bounce"):
+            _, st = cornell.trace_rays(r[key + "_rays"], stats=True)
+            assert st["rays"] == len(r[key + "_rays"])
+    finally:
+        ptb.set_option("count_visits", 0)
+
+
 def test_empty_and_tiny_inputs(cornell):
     assert len(cornell.trace_rays(np.zeros((0, 6), np.float32))) == 0
     one = cornell.trace_rays(np.array([[0, 2.3, 11.7, 0, 0, -1]], np.float32))
