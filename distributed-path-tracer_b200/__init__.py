@@ -121,7 +121,8 @@ HIT_DTYPE = np.dtype([("instance", "<u4"), ("surface", "<u4"), ("triangle", "<u4
 # Every symbol include/ptb.h declares (checked against the header by tests/test_abi.py).
 EXPORTS = [
     "ptb_scene_create", "ptb_scene_load_gltf", "ptb_scene_destroy", "ptb_scene_get_info", "ptb_scene_dump_kd",
-    "ptb_trace_rays", "ptb_trace_rays_attrs", "ptb_render_tile", "ptb_render_tile_dev", "ptb_tonemap_rgba8",
+    "ptb_trace_rays", "ptb_trace_rays_attrs", "ptb_trace_rays_dev", "ptb_shard_reset_dev", "ptb_shard_trace_dev",
+    "ptb_shard_publish_dev", "ptb_shard_unpack_dev", "ptb_render_tile", "ptb_render_tile_dev", "ptb_tonemap_rgba8",
     "ptb_write_png", "ptb_worker_run", "ptb_host_build_kd", "ptb_desc_load_gltf", "ptb_desc_get", "ptb_desc_free",
     "ptb_camera_rays", "ptb_trace_rays_stats", "ptb_extend_registers", "ptb_selftest_division", "ptb_set_option", "ptb_last_error",
     "ptb_abi_version", "ptb_device_count",
@@ -154,6 +155,17 @@ def lib():
     L.ptb_trace_rays.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_void_p]
     L.ptb_trace_rays_attrs.restype = st
     L.ptb_trace_rays_attrs.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_void_p, f32p]
+    L.ptb_trace_rays_dev.restype = st
+    L.ptb_trace_rays_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.ptb_shard_reset_dev.restype = st
+    L.ptb_shard_reset_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.ptb_shard_trace_dev.restype = st
+    L.ptb_shard_trace_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p), C.c_int,
+                                      C.c_void_p]
+    L.ptb_shard_publish_dev.restype = st
+    L.ptb_shard_publish_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    L.ptb_shard_unpack_dev.restype = st
+    L.ptb_shard_unpack_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.ptb_trace_rays_stats.restype = st
     L.ptb_trace_rays_stats.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_void_p, C.POINTER(RenderStats)]
     L.ptb_camera_rays.restype = st
@@ -440,6 +452,11 @@ class Scene:
             return hits, at
         _check(lib().ptb_trace_rays(self.h, _fp(od), len(od), hits.ctypes.data))
         return hits
+
+    def trace_rays_dev(self, rays_dev_ptr: int, n: int, hits_dev_ptr: int, stream: int = 0):
+        """Rays (n*6 float32) and hits (n ptb_hit records, HIT_DTYPE) stay in device memory; asynchronous."""
+        _check(lib().ptb_trace_rays_dev(self.h, C.c_void_p(rays_dev_ptr), n, C.c_void_p(hits_dev_ptr),
+                                        C.c_void_p(stream)))
 
     def camera_rays(self, w, h, px, py, aa):
         px = np.ascontiguousarray(px, np.uint32)

@@ -332,3 +332,56 @@ def merge_occlusion(occluded, device=None):
 def trace_rays_sharded(shard_scene, instance_map, origin_dir, device=None):
     """Closest hits of `origin_dir` (identical on every rank) against the union of all ranks' shards."""
     return merge_closest_hits(shard_scene.trace_rays(origin_dir), instance_map, device=device)
+
+
+class ShardMergeContext:
+    """Device-resident geometry-shard merge: the exchange step runs as 64-bit atomics and plain stores into the
+    other GPUs' memory over NVLink (``ptb_shard_*_dev``, include/ptb.h), not through NCCL.  The buffers are
+    ``torch.distributed._symmetric_memory`` allocations, so every rank knows every rank's device address;
+    ``torch.distributed`` (NCCL) is only the rendezvous."""
+
+    def __init__(self, shard_scene, instance_map, capacity: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.torch, self.dist, self.C = torch, dist, C
+        self.scene = shard_scene
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.capacity = int(capacity)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.keys = symm.empty(self.capacity, dtype=torch.int64, device=dev)
+        self.payload = symm.empty(self.capacity * 4, dtype=torch.int32, device=dev)
+        self.h_keys = symm.rendezvous(self.keys, self.group)
+        self.h_payload = symm.rendezvous(self.payload, self.group)
+        self.key_ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.h_keys.buffer_ptrs])
+        self.payload_ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.h_payload.buffer_ptrs])
+        self.instance_map = torch.from_numpy(np.ascontiguousarray(instance_map, np.uint32).view(np.int32)).to(dev)
+        if self.instance_map.numel() == 0:  # a shard may be empty; the kernel never dereferences the map then
+            self.instance_map = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def trace(self, rays_dev, hits_dev=None):
+        """rays_dev: float32 CUDA tensor [n, 6], identical on every rank.  → uint8 CUDA tensor [n, 28] holding
+        ptb_hit records (view it with HIT_DTYPE on the host): the closest hits against ALL ranks' shards."""
+        from . import lib, _check, HIT_DTYPE
+        torch, C = self.torch, self.C
+        n = int(rays_dev.shape[0])
+        if n > self.capacity:
+            raise ValueError("more rays than the merge buffers hold")
+        rays_dev = rays_dev.contiguous()
+        if hits_dev is None:
+            hits_dev = torch.empty((n, HIT_DTYPE.itemsize), dtype=torch.uint8, device=rays_dev.device)
+        st = torch.cuda.current_stream().cuda_stream
+        L = lib()
+        _check(L.ptb_shard_reset_dev(C.c_void_p(self.keys.data_ptr()), n, C.c_void_p(st)))
+        self.h_keys.barrier(channel=0)       # everybody's key buffer is reset before anybody merges into it
+        _check(L.ptb_shard_trace_dev(self.scene.h, C.c_void_p(rays_dev.data_ptr()), n,
+                                     C.c_void_p(self.instance_map.data_ptr()), self.key_ptrs, self.world, C.c_void_p(st)))
+        self.h_keys.barrier(channel=1)       # all minima have landed
+        _check(L.ptb_shard_publish_dev(self.scene.h, n, C.c_void_p(self.keys.data_ptr()), self.payload_ptrs,
+                                       self.world, C.c_void_p(st)))
+        self.h_payload.barrier(channel=0)    # the winners' payloads have landed
+        _check(L.ptb_shard_unpack_dev(C.c_void_p(self.keys.data_ptr()), C.c_void_p(self.payload.data_ptr()), n,
+                                      C.c_void_p(hits_dev.data_ptr()), C.c_void_p(st)))
+        return hits_dev

@@ -187,6 +187,34 @@ ptb_status ptb_render_tile_dev(const ptb_scene* scene, const ptb_tile_req* req, 
     });
 }
 
+ptb_status ptb_trace_rays_dev(const ptb_scene* scene, const float* origin_dir_dev, uint64_t n, ptb_hit* hits_dev,
+                              void* stream) {
+    return guarded([&] { ptb::trace_rays_dev(scene, origin_dir_dev, n, hits_dev, static_cast<cudaStream_t>(stream)); });
+}
+
+ptb_status ptb_shard_reset_dev(uint64_t* keys_dev, uint64_t n, void* stream) {
+    return guarded([&] { ptb::shard_reset_dev(keys_dev, n, static_cast<cudaStream_t>(stream)); });
+}
+
+ptb_status ptb_shard_trace_dev(const ptb_scene* shard, const float* origin_dir_dev, uint64_t n,
+                               const uint32_t* instance_map_dev, void* const* peer_keys, int world, void* stream) {
+    return guarded([&] {
+        ptb::shard_trace_dev(shard, origin_dir_dev, n, instance_map_dev, peer_keys, world, static_cast<cudaStream_t>(stream));
+    });
+}
+
+ptb_status ptb_shard_publish_dev(const ptb_scene* shard, uint64_t n, const uint64_t* best_keys_dev,
+                                 void* const* peer_payload, int world, void* stream) {
+    return guarded([&] {
+        ptb::shard_publish_dev(shard, n, best_keys_dev, peer_payload, world, static_cast<cudaStream_t>(stream));
+    });
+}
+
+ptb_status ptb_shard_unpack_dev(const uint64_t* best_keys_dev, const void* payload_dev, uint64_t n, ptb_hit* hits_dev,
+                                void* stream) {
+    return guarded([&] { ptb::shard_unpack_dev(best_keys_dev, payload_dev, n, hits_dev, static_cast<cudaStream_t>(stream)); });
+}
+
 ptb_status ptb_tonemap_rgba8(const float* rgb, const float* alpha, uint64_t n_pixels, uint8_t* rgba8_out) {
     return guarded([&] { ptb::tonemap_host(rgb, alpha, n_pixels, rgba8_out); });
 }

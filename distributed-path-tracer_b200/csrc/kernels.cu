@@ -597,6 +597,86 @@ void launch_export_hits(const DScene& S, const uint4* hits, const float* t, uint
                                                                    attrs_out);
 }
 
+// ---- geometry-shard merge over peer memory (cluster.py: trace_rays_sharded_dev) -------------------------------
+// key = distance bits << 32 | global instance << 12 | surface; a miss is the largest key.  Distances of hits are
+// non-negative floats, whose bits order like the numbers, and renderer::intersect keeps the first instance in
+// scene order on equal distances (strict <, renderer.cpp:663-669): the integer minimum of the keys over all
+// shards IS the unsharded answer.
+constexpr unsigned long long MERGE_MISS_KEY = 0x7FFFFFFFFFFFFFFFull;
+
+__global__ void shard_keys_kernel(const uint4* __restrict__ hits, const float* __restrict__ t, uint64_t n,
+                                  const uint32_t* __restrict__ instance_map, unsigned long long* __restrict__ local_keys,
+                                  ShardPeers peers) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 h = hits[i];
+        unsigned long long key = MERGE_MISS_KEY;
+        if (h.x != HIT_MISS) {
+            const uint32_t inst = instance_map[h.x >> HIT_SURFACE_BITS], surf = h.x & ((1u << HIT_SURFACE_BITS) - 1u);
+            key = ((unsigned long long)__float_as_uint(t[i]) << 32) | ((unsigned long long)inst << HIT_SURFACE_BITS) | surf;
+            // the exchange step: one 64-bit minimum per peer, straight into that GPU's memory over NVLink
+            for (int r = 0; r < peers.world; r++) atomicMin_system(peers.keys[r] + i, key);
+        }
+        local_keys[i] = key;
+    }
+}
+
+__global__ void shard_payload_kernel(const uint4* __restrict__ hits, const unsigned long long* __restrict__ local_keys,
+                                     const unsigned long long* __restrict__ best_keys, uint64_t n, ShardPeers peers) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = local_keys[i];
+        if (key == MERGE_MISS_KEY || key != best_keys[i]) continue;
+        // exactly one shard owns the winning instance: plain stores, no race
+        const uint4 h = hits[i];
+        const uint4 pay = make_uint4(h.y, h.z, h.w, 0u); // triangle, beta, gamma
+        for (int r = 0; r < peers.world; r++) peers.payload[r][i] = pay;
+    }
+}
+
+__global__ void shard_unpack_kernel(const unsigned long long* __restrict__ best_keys, const uint4* __restrict__ payload,
+                                    uint64_t n, ptb_hit* __restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = best_keys[i];
+        ptb_hit o;
+        if (key == MERGE_MISS_KEY) {
+            o.instance = o.surface = o.triangle = PTB_MISS;
+            o.t = -1.0f;
+            o.bary[0] = o.bary[1] = o.bary[2] = 0.0f;
+        } else {
+            const uint32_t low = (uint32_t)key;
+            const uint4 pay = payload[i];
+            const float beta = __uint_as_float(pay.y), gamma = __uint_as_float(pay.z);
+            o.instance = low >> HIT_SURFACE_BITS;
+            o.surface = low & ((1u << HIT_SURFACE_BITS) - 1u);
+            o.triangle = pay.x;
+            o.t = __uint_as_float((uint32_t)(key >> 32));
+            o.bary[0] = 1 - beta - gamma;
+            o.bary[1] = beta;
+            o.bary[2] = gamma;
+        }
+        out[i] = o;
+    }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, uint64_t n, unsigned long long v) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+void launch_shard_keys(const uint4* hits, const float* t, uint64_t n, const uint32_t* instance_map,
+                       unsigned long long* local_keys, const ShardPeers& peers, cudaStream_t st) {
+    shard_keys_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(hits, t, n, instance_map, local_keys, peers);
+}
+void launch_shard_payload(const uint4* hits, const unsigned long long* local_keys, const unsigned long long* best_keys,
+                          uint64_t n, const ShardPeers& peers, cudaStream_t st) {
+    shard_payload_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(hits, local_keys, best_keys, n, peers);
+}
+void launch_shard_unpack(const unsigned long long* best_keys, const uint4* payload, uint64_t n, void* hits_out,
+                         cudaStream_t st) {
+    shard_unpack_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(best_keys, payload, n, static_cast<ptb_hit*>(hits_out));
+}
+void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st) {
+    fill_u64_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(p, n, v);
+}
+
 void launch_camera_rays(const DScene& S, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py, const float* aa,
                         uint64_t n, float* origin_dir, cudaStream_t st) {
     camera_rays_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(S, w, h, px, py, aa, n, origin_dir);

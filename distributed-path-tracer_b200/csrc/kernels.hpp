@@ -80,6 +80,21 @@ void launch_export_hits(const DScene& S, const uint4* hits, const float* t, uint
 void launch_camera_rays(const DScene& S, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py,
                         const float* aa, uint64_t n, float* origin_dir, cudaStream_t st);
 
+// geometry-shard merge over peer memory: every rank's key / payload buffer (symmetric allocations), by value
+constexpr int SHARD_MAX_WORLD = 16;
+struct ShardPeers {
+    int world;
+    unsigned long long* keys[SHARD_MAX_WORLD];
+    uint4* payload[SHARD_MAX_WORLD];
+};
+void launch_shard_keys(const uint4* hits, const float* t, uint64_t n, const uint32_t* instance_map,
+                       unsigned long long* local_keys, const ShardPeers& peers, cudaStream_t st);
+void launch_shard_payload(const uint4* hits, const unsigned long long* local_keys, const unsigned long long* best_keys,
+                          uint64_t n, const ShardPeers& peers, cudaStream_t st);
+void launch_shard_unpack(const unsigned long long* best_keys, const uint4* payload, uint64_t n, void* hits_out,
+                         cudaStream_t st);
+void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st);
+
 // extend.cu — the lane-state-machine closest-hit kernel (default); launch_extend is the first, simple kernel
 void launch_extend_lanes(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
                          const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,

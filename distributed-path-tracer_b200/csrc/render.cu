@@ -346,6 +346,105 @@ void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, pt
     }
 }
 
+// ---- device-resident closest hit and the geometry-shard merge ------------------------------------------------
+
+namespace {
+
+// prep + extend for rays that are already in device memory; hit records stay in the workspace (w.hits, w.t)
+void trace_into_workspace(const ptb_scene* s, Workspace& w, const float* rays_dev, uint64_t n, cudaStream_t st) {
+    w.path[0][0].ensure(n * sizeof(float4));
+    w.path[0][1].ensure(n * sizeof(float4));
+    w.hits.ensure(n * sizeof(uint4));
+    w.t.ensure(n * sizeof(float));
+    w.qcount.ensure((1 + QHEAD_STRIDE) * sizeof(uint32_t));
+    w.counters.ensure(sizeof(DeviceCounters));
+    uint32_t* qc = (uint32_t*)w.qcount.p;
+    const uint32_t n32 = (uint32_t)n;
+    PTB_CUDA(cudaMemsetAsync(qc, 0, (1 + QHEAD_STRIDE) * sizeof(uint32_t), st));
+    PTB_CUDA(cudaMemcpyAsync(qc, &n32, sizeof(n32), cudaMemcpyHostToDevice, st));
+    PTB_CUDA(cudaStreamSynchronize(st)); // n32 lives on this stack frame
+    PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
+    launch_prep_rays(rays_dev, n, (float4*)w.path[0][0].p, (float4*)w.path[0][1].p, st);
+    run_extend(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint4*)w.hits.p, (float*)w.t.p,
+               &qc[0], &qc[1], (DeviceCounters*)w.counters.p, launch_cfg(s), st);
+}
+
+void check_rays(const ptb_scene* s, const void* a, const void* b, uint64_t n) {
+    if (!s) throw Error(PTB_E_INVALID, "scene is NULL");
+    if (n && (!a || !b)) throw Error(PTB_E_INVALID, "NULL device pointer");
+    if (n >= (1ull << 31)) throw Error(PTB_E_INVALID, "too many rays in one call (max 2^31 - 1)");
+}
+
+ShardPeers make_peers(void* const* keys, void* const* payload, int world) {
+    if (world < 1 || world > SHARD_MAX_WORLD) throw Error(PTB_E_INVALID, "world size out of range (1..16)");
+    ShardPeers p{};
+    p.world = world;
+    for (int r = 0; r < world; r++) {
+        if ((keys && !keys[r]) || (payload && !payload[r])) throw Error(PTB_E_INVALID, "NULL peer buffer");
+        p.keys[r] = keys ? static_cast<unsigned long long*>(keys[r]) : nullptr;
+        p.payload[r] = payload ? static_cast<uint4*>(payload[r]) : nullptr;
+    }
+    return p;
+}
+
+} // namespace
+
+void trace_rays_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, ptb_hit* hits_dev, cudaStream_t st) {
+    check_rays(s, rays_dev, hits_dev, n);
+    if (n == 0) return;
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device, st);
+    std::lock_guard<std::mutex> guard(w.lock);
+    trace_into_workspace(s, w, rays_dev, n, st);
+    launch_export_hits(s->d, (const uint4*)w.hits.p, (const float*)w.t.p, n, hits_dev, nullptr, st);
+    PTB_CUDA(cudaGetLastError());
+}
+
+void shard_reset_dev(uint64_t* keys_dev, uint64_t n, cudaStream_t st) {
+    if (n && !keys_dev) throw Error(PTB_E_INVALID, "NULL device pointer");
+    if (n) launch_fill_u64(reinterpret_cast<unsigned long long*>(keys_dev), n, 0x7FFFFFFFFFFFFFFFull, st);
+    PTB_CUDA(cudaGetLastError());
+}
+
+void shard_trace_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, const uint32_t* instance_map_dev,
+                     void* const* peer_keys, int world, cudaStream_t st) {
+    check_rays(s, rays_dev, instance_map_dev, n);
+    const ShardPeers peers = make_peers(peer_keys, nullptr, world);
+    if (n == 0) return;
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device, st);
+    std::lock_guard<std::mutex> guard(w.lock);
+    trace_into_workspace(s, w, rays_dev, n, st);
+    w.io_c.ensure(n * sizeof(unsigned long long));
+    launch_shard_keys((const uint4*)w.hits.p, (const float*)w.t.p, n, instance_map_dev, (unsigned long long*)w.io_c.p,
+                      peers, st);
+    PTB_CUDA(cudaGetLastError());
+}
+
+void shard_publish_dev(const ptb_scene* s, uint64_t n, const uint64_t* best_keys_dev, void* const* peer_payload, int world,
+                       cudaStream_t st) {
+    check_rays(s, best_keys_dev, peer_payload, n);
+    const ShardPeers peers = make_peers(nullptr, peer_payload, world);
+    if (n == 0) return;
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device, st);
+    std::lock_guard<std::mutex> guard(w.lock);
+    if (w.hits.bytes < n * sizeof(uint4) || w.io_c.bytes < n * sizeof(unsigned long long))
+        throw Error(PTB_E_INVALID, "ptb_shard_publish_dev without a matching ptb_shard_trace_dev on this stream");
+    launch_shard_payload((const uint4*)w.hits.p, (const unsigned long long*)w.io_c.p,
+                         reinterpret_cast<const unsigned long long*>(best_keys_dev), n, peers, st);
+    PTB_CUDA(cudaGetLastError());
+}
+
+void shard_unpack_dev(const uint64_t* best_keys_dev, const void* payload_dev, uint64_t n, ptb_hit* hits_dev,
+                      cudaStream_t st) {
+    if (n && (!best_keys_dev || !payload_dev || !hits_dev)) throw Error(PTB_E_INVALID, "NULL device pointer");
+    if (n)
+        launch_shard_unpack(reinterpret_cast<const unsigned long long*>(best_keys_dev), static_cast<const uint4*>(payload_dev),
+                            n, hits_dev, st);
+    PTB_CUDA(cudaGetLastError());
+}
+
 void camera_rays_host(const ptb_scene* s, uint32_t wd, uint32_t ht, const uint32_t* px, const uint32_t* py,
                       const float* aa, uint64_t n, float* origin_dir) {
     if (!s) throw Error(PTB_E_INVALID, "scene is NULL");

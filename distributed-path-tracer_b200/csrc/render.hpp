@@ -31,6 +31,14 @@ void render_tile_host(const ptb_scene* s, const ptb_tile_req& req, float* rgb_ou
                       ptb_render_stats* stats);
 void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, ptb_hit* hits_out, float* attrs_out,
                      ptb_render_stats* stats);
+void trace_rays_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, ptb_hit* hits_dev, cudaStream_t st);
+void shard_reset_dev(uint64_t* keys_dev, uint64_t n, cudaStream_t st);
+void shard_trace_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, const uint32_t* instance_map_dev,
+                     void* const* peer_keys, int world, cudaStream_t st);
+void shard_publish_dev(const ptb_scene* s, uint64_t n, const uint64_t* best_keys_dev, void* const* peer_payload, int world,
+                       cudaStream_t st);
+void shard_unpack_dev(const uint64_t* best_keys_dev, const void* payload_dev, uint64_t n, ptb_hit* hits_dev,
+                      cudaStream_t st);
 void camera_rays_host(const ptb_scene* s, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py,
                       const float* aa, uint64_t n, float* origin_dir);
 void tonemap_host(const float* rgb, const float* alpha, uint64_t n, uint8_t* rgba8);

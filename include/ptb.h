@@ -310,6 +310,36 @@ ptb_status ptb_camera_rays(const ptb_scene* scene, uint32_t w, uint32_t h, const
 ptb_status ptb_trace_rays_stats(const ptb_scene* scene, const float* origin_dir, uint64_t n,
                                 ptb_hit* hits_out, ptb_render_stats* stats_out);
 
+/* ptb_trace_rays with rays (n * 6 floats) and hits in DEVICE memory, asynchronous on `stream`
+ * (a cudaStream_t; NULL = the default stream).  No host copy. */
+ptb_status ptb_trace_rays_dev(const ptb_scene* scene, const float* origin_dir_dev, uint64_t n, ptb_hit* hits_dev,
+                              void* stream);
+
+/* Geometry-sharded closest hit — the reference's own distribution model
+ * (APP/processors/worker/intersection_worker.cpp:69-147: every worker holds part of the geometry, every ray
+ * visits every worker, the nearest result wins).  One process per GPU; each holds a SHARD scene (a subset
+ * of the instances) and, in peer-mapped (symmetric) memory, a key buffer (n uint64) and a payload buffer
+ * (n * 16 bytes) whose device addresses on every rank are known to all ranks.
+ *   1. ptb_shard_reset_dev          own key buffer := "miss"                       -- then a barrier
+ *   2. ptb_shard_trace_dev          trace the rays against the shard, and min-merge  key = t_bits << 32 |
+ *                                   global instance << 12 | surface  into EVERY rank's key buffer with 64-bit
+ *                                   atomics over NVLink (the exchange step; no NCCL)  -- then a barrier
+ *   3. ptb_shard_publish_dev        the rank whose key won stores triangle + barycentrics into every
+ *                                   rank's payload buffer                           -- then a barrier
+ *   4. ptb_shard_unpack_dev         merged keys + payload -> ptb_hit records (global instance indices)
+ * The result is bit-identical to ptb_trace_rays on the unsharded scene: hit distances are non-negative floats
+ * (their bits order like the numbers) and renderer::intersect keeps the first instance in scene order on
+ * equal distances (renderer.cpp:663-669).  instance_map_dev: shard-local -> global instance index.
+ * peer_keys / peer_payload: HOST arrays of `world` device pointers (rank order).  Steps 2 and 3 must use the
+ * same stream. */
+ptb_status ptb_shard_reset_dev(uint64_t* keys_dev, uint64_t n, void* stream);
+ptb_status ptb_shard_trace_dev(const ptb_scene* shard, const float* origin_dir_dev, uint64_t n,
+                               const uint32_t* instance_map_dev, void* const* peer_keys, int world, void* stream);
+ptb_status ptb_shard_publish_dev(const ptb_scene* shard, uint64_t n, const uint64_t* best_keys_dev,
+                                 void* const* peer_payload, int world, void* stream);
+ptb_status ptb_shard_unpack_dev(const uint64_t* best_keys_dev, const void* payload_dev, uint64_t n, ptb_hit* hits_dev,
+                                void* stream);
+
 /* Registers per thread of the extend kernel as loaded (cudaFuncGetAttributes). */
 int ptb_extend_registers(void);
 

@@ -276,6 +276,23 @@ def test_geometry_shards_merge_to_the_unsharded_answer(ptb, procedural, world):
     assert not (want["instance"] == 22).any() and (want["instance"] == 4).any()
 
 
+def test_peer_memory_shard_merge_on_two_gpus(ptb):
+    """The device-resident merge (ptb_shard_*_dev: 64-bit minima straight into the other GPUs' memory) against the
+    unsharded search, bit for bit — needs two GPUs (scripts/shard_merge_check.py under torchrun); skipped on one."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "scripts", "shard_merge_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "sharded+merged == unsharded: True" in r.stdout
+
+
 def test_instrumented_kernel_finds_no_bound_violation(ptb, procedural, cornell):
     """compute-sanitizer is not available on the GPU pool, so the instrumented build of the extend kernel
     (count_visits) checks every pair / reference / triangle index and the traversal-stack height itself and the
