@@ -602,8 +602,6 @@ void launch_export_hits(const DScene& S, const uint4* hits, const float* t, uint
 // non-negative floats, whose bits order like the numbers, and renderer::intersect keeps the first instance in
 // scene order on equal distances (strict <, renderer.cpp:663-669): the integer minimum of the keys over all
 // shards IS the unsharded answer.
-constexpr unsigned long long MERGE_MISS_KEY = 0x7FFFFFFFFFFFFFFFull;
-
 __global__ void shard_keys_kernel(const uint4* __restrict__ hits, const float* __restrict__ t, uint64_t n,
                                   const uint32_t* __restrict__ instance_map, unsigned long long* __restrict__ local_keys,
                                   ShardPeers peers) {

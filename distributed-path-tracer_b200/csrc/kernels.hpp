@@ -87,6 +87,14 @@ struct ShardPeers {
     unsigned long long* keys[SHARD_MAX_WORLD];
     uint4* payload[SHARD_MAX_WORLD];
 };
+// what the fused extend kernel needs to publish its results (device memory, read at result-write time only)
+struct MergeArgs {
+    ShardPeers peers;
+    const uint32_t* instance_map;   // shard-local → global instance index
+    unsigned long long* local_keys; // this rank's own key per ray (ptb_shard_publish_dev compares against it)
+};
+constexpr unsigned long long MERGE_MISS_KEY = 0x7FFFFFFFFFFFFFFFull;
+
 void launch_shard_keys(const uint4* hits, const float* t, uint64_t n, const uint32_t* instance_map,
                        unsigned long long* local_keys, const ShardPeers& peers, cudaStream_t st);
 void launch_shard_payload(const uint4* hits, const unsigned long long* local_keys, const unsigned long long* best_keys,
@@ -99,6 +107,11 @@ void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cu
 void launch_extend_lanes(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
                          const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
                          cudaStream_t st);
+// the same kernel with the geometry-shard exchange fused into its result write: every finished ray's key goes
+// straight into all ranks' key buffers (64-bit atomicMin over NVLink) — compute and collective in one kernel
+void launch_extend_lanes_merge(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
+                               const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const MergeArgs* merge_dev,
+                               const LaunchCfg& cfg, cudaStream_t st);
 int extend_lanes_regs_per_thread();
 // extend_coop.cu — lane state machine + warp-cooperative leaf tests
 void launch_extend_coop(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,

@@ -351,7 +351,8 @@ void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, pt
 namespace {
 
 // prep + extend for rays that are already in device memory; hit records stay in the workspace (w.hits, w.t)
-void trace_into_workspace(const ptb_scene* s, Workspace& w, const float* rays_dev, uint64_t n, cudaStream_t st) {
+void trace_into_workspace(const ptb_scene* s, Workspace& w, const float* rays_dev, uint64_t n, cudaStream_t st,
+                          const MergeArgs* merge_dev = nullptr) {
     w.path[0][0].ensure(n * sizeof(float4));
     w.path[0][1].ensure(n * sizeof(float4));
     w.hits.ensure(n * sizeof(uint4));
@@ -365,8 +366,13 @@ void trace_into_workspace(const ptb_scene* s, Workspace& w, const float* rays_de
     PTB_CUDA(cudaStreamSynchronize(st)); // n32 lives on this stack frame
     PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
     launch_prep_rays(rays_dev, n, (float4*)w.path[0][0].p, (float4*)w.path[0][1].p, st);
-    run_extend(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint4*)w.hits.p, (float*)w.t.p,
-               &qc[0], &qc[1], (DeviceCounters*)w.counters.p, launch_cfg(s), st);
+    if (merge_dev)
+        launch_extend_lanes_merge(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint4*)w.hits.p,
+                                  (float*)w.t.p, &qc[0], &qc[1], (DeviceCounters*)w.counters.p, merge_dev, launch_cfg(s),
+                                  st);
+    else
+        run_extend(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint4*)w.hits.p, (float*)w.t.p,
+                   &qc[0], &qc[1], (DeviceCounters*)w.counters.p, launch_cfg(s), st);
 }
 
 void check_rays(const ptb_scene* s, const void* a, const void* b, uint64_t n) {
@@ -414,10 +420,19 @@ void shard_trace_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, cons
     PTB_CUDA(cudaSetDevice(s->device));
     Workspace& w = workspace(s->device, st);
     std::lock_guard<std::mutex> guard(w.lock);
-    trace_into_workspace(s, w, rays_dev, n, st);
     w.io_c.ensure(n * sizeof(unsigned long long));
-    launch_shard_keys((const uint4*)w.hits.p, (const float*)w.t.p, n, instance_map_dev, (unsigned long long*)w.io_c.p,
-                      peers, st);
+    if (g_options.extend_variant == 1 && !g_options.count_visits) {
+        // default kernel: the exchange is fused into extend's result write (one kernel: compute + collective)
+        MergeArgs args{peers, instance_map_dev, (unsigned long long*)w.io_c.p};
+        w.io_b.ensure(sizeof(MergeArgs));
+        PTB_CUDA(cudaMemcpyAsync(w.io_b.p, &args, sizeof(args), cudaMemcpyHostToDevice, st));
+        PTB_CUDA(cudaStreamSynchronize(st)); // args lives on this stack frame
+        trace_into_workspace(s, w, rays_dev, n, st, (const MergeArgs*)w.io_b.p);
+    } else {
+        trace_into_workspace(s, w, rays_dev, n, st);
+        launch_shard_keys((const uint4*)w.hits.p, (const float*)w.t.p, n, instance_map_dev,
+                          (unsigned long long*)w.io_c.p, peers, st);
+    }
     PTB_CUDA(cudaGetLastError());
 }
 
