@@ -227,7 +227,10 @@ def run_ptb(args):
     t_build = time.perf_counter() - t_build
     ptb.set_option("wave_paths", args.wave_paths)
 
-    cols, rows = cluster.tile_grid_for(world, args.tiles_per_gpu)
+    # tiles per GPU: as many as asked for, but a tile keeps at least ~2 M paths (a small frame is not shredded)
+    paths_per_gpu = full_w * full_h * spp0
+    tiles_per_gpu = max(1, min(args.tiles_per_gpu, max(8, paths_per_gpu // (2 << 20))))
+    cols, rows = cluster.tile_grid_for(world, tiles_per_gpu)
     tiles = cluster.make_tiles(full_w, full_h, cols, rows)
     frame = torch.zeros((full_h, full_w, 4), dtype=torch.float32, device=dev)
     n_workers = max(1, args.streams)
