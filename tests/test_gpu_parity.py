@@ -276,6 +276,43 @@ def test_geometry_shards_merge_to_the_unsharded_answer(ptb, procedural, world):
     assert not (want["instance"] == 22).any() and (want["instance"] == 4).any()
 
 
+def test_device_resident_trace_and_single_rank_shard_merge(ptb, cornell):
+    """ptb_trace_rays_dev (rays and hits stay on the device) and the ptb_shard_*_dev pipeline with world = 1 (the peer
+    buffers are this GPU's own) return exactly what ptb_trace_rays returns."""
+    import ctypes as C
+    import torch
+    r = H.load("cornell_rays.npz")
+    od = np.ascontiguousarray(np.concatenate([r["cam_rays"], r["rnd_rays"], r["bounce_rays"]]), np.float32)
+    want = cornell.trace_rays(od)
+    n = len(od)
+    rays = torch.from_numpy(od).cuda()
+    hits = torch.zeros((n, ptb.HIT_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    cornell.trace_rays_dev(rays.data_ptr(), n, hits.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    H.assert_hits_equal(hits.cpu().numpy().view(ptb.HIT_DTYPE).reshape(-1), want, "trace_rays_dev")
+    # shard pipeline, one rank: identity instance map, own buffers as the only peer
+    L = ptb.lib()
+    keys = torch.zeros(n, dtype=torch.int64, device="cuda")
+    payload = torch.zeros(n * 4, dtype=torch.int32, device="cuda")
+    imap = torch.arange(cornell.info()["n_instances"], dtype=torch.int32, device="cuda")
+    kp = (C.c_void_p * 1)(keys.data_ptr())
+    pp = (C.c_void_p * 1)(payload.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.zeros_like(hits)
+    for variant in (1, 3):  # fused exchange in the default kernel; separate key kernel behind any other
+        ptb.set_option("extend_variant", variant)
+        try:
+            assert L.ptb_shard_reset_dev(C.c_void_p(keys.data_ptr()), n, st) == 0
+            assert L.ptb_shard_trace_dev(cornell.h, C.c_void_p(rays.data_ptr()), n, C.c_void_p(imap.data_ptr()), kp, 1, st) == 0
+            assert L.ptb_shard_publish_dev(cornell.h, n, C.c_void_p(keys.data_ptr()), pp, 1, st) == 0
+            assert L.ptb_shard_unpack_dev(C.c_void_p(keys.data_ptr()), C.c_void_p(payload.data_ptr()), n,
+                                          C.c_void_p(out.data_ptr()), st) == 0
+        finally:
+            ptb.set_option("extend_variant", 1)
+        torch.cuda.synchronize()
+        H.assert_hits_equal(out.cpu().numpy().view(ptb.HIT_DTYPE).reshape(-1), want, f"shard pipeline, variant {variant}")
+
+
 def test_peer_memory_shard_merge_on_two_gpus(ptb):
     """The device-resident merge (ptb_shard_*_dev: 64-bit minima straight into the other GPUs' memory) against the
     unsharded search, bit for bit — needs two GPUs (scripts/shard_merge_check.py under torchrun); skipped on one."""
