@@ -405,7 +405,7 @@ def main():
     ap.add_argument("--tiles-per-gpu", type=int, default=32,
                     help="tiles per GPU (work-stolen); more tiles = a shorter tail when ranks finish unevenly")
     ap.add_argument("--wave-paths", type=int, default=8 << 20)
-    ap.add_argument("--streams", type=int, default=4, help="tiles in flight per GPU (host threads / CUDA streams)")
+    ap.add_argument("--streams", type=int, default=6, help="tiles in flight per GPU (host threads / CUDA streams)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
