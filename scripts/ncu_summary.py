@@ -19,12 +19,18 @@ idx = {h: i for i, h in enumerate(hdr)}
 for w in want:
     if w in idx:
         print(w.ljust(72), [r[idx[w]] for r in rows[2:]], units[idx[w]])
-print("-- stall reasons (per warp active, pct)")
+print("-- stall cycles per issued instruction (smsp__average_warps_issue_stalled_*_per_issue_active), >= 0.1")
 for h in hdr:
-    if h.startswith('smsp__warp_issue_stalled') and h.endswith('per_warp_active.pct'):
+    if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio'):
         vals = [r[idx[h]] for r in rows[2:]]
         try:
-            if max(float(v.replace(',', '')) for v in vals) >= 3.0:
-                print(h[len('smsp__warp_issue_stalled_'):-len('_per_warp_active.pct')].ljust(30), vals)
+            if max(float(v.replace(',', '')) for v in vals) >= 0.1:
+                print(h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')].ljust(30), vals)
         except ValueError:
             pass
+print("-- L1 by memory space")
+for w in ['l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct', 'l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct',
+          'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum',
+          'l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum']:
+    if w in idx:
+        print(w.ljust(72), [r[idx[w]] for r in rows[2:]], units[idx[w]])
