@@ -347,6 +347,13 @@ def run_ptb(args):
                 tj = json.load(open(prof))
                 roofline["traffic"] = tj["dram_bytes_per_ray"] * roofline["rays_per_launch"]
                 roofline["traffic_source"] = "profiles/extend_traffic.json: dram bytes/ray under ncu x rays_per_launch"
+                # what actually bounds the kernel (SURVEY 8d asks for the issue-rate view next to the HBM one):
+                # from the same ncu capture, per extend launch of a wave (primary, bounce 1..3)
+                roofline["issue"] = {"slots_busy_pct": tj.get("issue_slots_busy_pct_per_launch"),
+                                     "active_lanes_per_instruction": tj.get("active_lanes_per_instruction_per_launch"),
+                                     "long_scoreboard_cycles_per_instruction":
+                                         tj.get("stall_cycles_per_instruction_long_scoreboard_per_launch"),
+                                     "source": "profiles/r01_v7_extend_ncu_summary.txt"}
             except Exception:
                 pass
 
