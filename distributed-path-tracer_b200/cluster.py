@@ -196,6 +196,7 @@ def broadcast_description(desc, src: int = 0):
                                                             for i, x in enumerate(desc.sun)),
                     environment_factor=desc.environment_factor, transparent_background=desc.transparent_background,
                     kd_use_sah=desc.kd_use_sah, kd_max_depth=desc.kd_max_depth,
+                    environment_texture=getattr(desc, "environment_texture", None),
                     textures=[(t["pixels"].shape, str(t["pixels"].dtype), bool(t.get("srgb", False)))
                               for t in desc.textures])
         arrays += [np.ascontiguousarray(t["pixels"]) for t in desc.textures]
@@ -223,7 +224,8 @@ def broadcast_description(desc, src: int = 0):
     textures = [dict(pixels=next(it), srgb=srgb) for (_, _, srgb) in meta["textures"]]
     return SceneDescription(meshes, np.array(meta["surfaces"], np.uint32).reshape(-1, 2), meta["instances"],
                             meta["materials"], meta["camera"], meta["sun"], meta["environment_factor"],
-                            meta["transparent_background"], meta["kd_use_sah"], meta["kd_max_depth"], textures)
+                            meta["transparent_background"], meta["kd_use_sah"], meta["kd_max_depth"], textures,
+                            environment_texture=meta.get("environment_texture"))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -265,7 +267,8 @@ def shard_instances(desc, rank: int, world_size: int):
         instances.append((o, b, new_first, count))
     shard = SceneDescription(meshes, np.array(surfaces, np.uint32).reshape(-1, 2), instances, desc.materials,
                              desc.camera, desc.sun, desc.environment_factor, desc.transparent_background,
-                             desc.kd_use_sah, desc.kd_max_depth, desc.textures)
+                             desc.kd_use_sah, desc.kd_max_depth, desc.textures,
+                             environment_texture=getattr(desc, "environment_texture", None))
     return shard, np.array(keep, np.uint32)
 
 

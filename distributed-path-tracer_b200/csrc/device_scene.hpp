@@ -106,6 +106,7 @@ struct DScene {
     DCamera camera;
     DSun sun;
     V3 environment;
+    uint32_t environment_tex; // 0xFFFFFFFF: none; else the equirectangular map a missing ray samples
     uint32_t transparent_background;
 };
 

@@ -201,8 +201,14 @@ __device__ __forceinline__ bool shade_path(const DScene& S, const WaveGeom& g, c
     const bool primary = (st.flags & F_PRIMARY) != 0;
     const float bg_alpha = S.transparent_background ? 0.0f : 1.0f;
 
-    if (hit.x == HIT_MISS) { // renderer.cpp:443-451, worker.cpp:307-317 (environment texture: not supported)
-        st.rad = st.rad + st.thr * S.environment;
+    if (hit.x == HIT_MISS) { // renderer.cpp:443-451, worker.cpp:307-317
+        V3 env = S.environment;
+        if (S.environment_tex != 0xFFFFFFFFu) { // equirectangular_proj, LIB/core/utils.hpp:22-27
+            const float eu = atan2f(st.d.z, st.d.x) * 0.1591F + 0.5F, ev = asinf(st.d.y) * 0.3183F + 0.5F;
+            const float4 c = tex_sample(S, S.environment_tex, eu, ev);
+            env = V3{c.x, c.y, c.z} * S.environment;
+        }
+        st.rad = st.rad + st.thr * env;
         const float a = APP_RR ? bg_alpha : (primary ? bg_alpha : 1.0f);
         result = make_float4(st.rad.x, st.rad.y, st.rad.z, a);
         return false;

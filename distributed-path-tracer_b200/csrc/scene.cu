@@ -159,6 +159,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
     require(desc.n_instances == 0 || desc.instances, "instances is NULL");
     require(desc.n_materials == 0 || desc.materials, "materials is NULL");
     require(desc.n_textures == 0 || desc.textures, "textures is NULL");
+    require(desc.environment_tex_plus1 <= desc.n_textures, "environment texture id out of range");
     require(desc.n_instances < (1u << (32 - HIT_SURFACE_BITS)), "too many instances (max 2^20 - 1)");
     const uint32_t max_depth = desc.kd_max_depth ? desc.kd_max_depth : 25;
     require(max_depth <= 25, "kd_max_depth above 25 is not supported (traversal stack depth)");
@@ -405,6 +406,7 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
             d.sun.angular_radius = 0;
         }
         d.environment = V3{desc.environment_factor[0], desc.environment_factor[1], desc.environment_factor[2]};
+        d.environment_tex = desc.environment_tex_plus1 ? desc.environment_tex_plus1 - 1 : 0xFFFFFFFFu;
         d.transparent_background = desc.transparent_background ? 1 : 0;
         PTB_CUDA(cudaDeviceSynchronize());
         s->info.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();

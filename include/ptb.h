@@ -132,6 +132,9 @@ typedef struct ptb_scene_desc {
     uint32_t transparent_background; /* renderer.hpp:30                      */
     uint32_t kd_use_sah;  /* mesh::build_kd_tree(use_sah=true, ...)          */
     uint32_t kd_max_depth; /* ... max_depth=25  (LIB/core/mesh.hpp:34); 0 → 25 */
+    uint32_t environment_tex_plus1; /* renderer.hpp:28 `environment`: 1 + index of the equirectangular
+                                       texture a missing ray samples (renderer.cpp:446-448,
+                                       worker.cpp:308-311); 0 = none (environment_factor alone) */
 } ptb_scene_desc;
 
 typedef struct ptb_scene ptb_scene;

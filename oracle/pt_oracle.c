@@ -131,6 +131,7 @@ typedef struct po_scene {
     v3 sun_dir, sun_energy;
     float sun_radius;
     v3 environment;
+    uint32_t environment_tex; /* PTB_NO_TEXTURE: none */
     int transparent;
 } po_scene;
 
@@ -443,6 +444,7 @@ po_scene* po_scene_create(const ptb_scene_desc* d) {
         s->sun_radius = d->sun.angular_radius;
     }
     s->environment = V(d->environment_factor[0], d->environment_factor[1], d->environment_factor[2]);
+    s->environment_tex = d->environment_tex_plus1 ? d->environment_tex_plus1 - 1 : PTB_NO_TEXTURE;
     s->transparent = d->transparent_background != 0;
     return s;
 }
@@ -883,13 +885,22 @@ static v3 direct_term(const po_scene* s, v3 n, v3 o, v3 l, const mat_t* m, float
     return clamp3(out, V(0, 0, 0), s->sun_energy);
 }
 
+/* What a ray that hits nothing receives: renderer.cpp:446-450 / worker.cpp:308-313 with equirectangular_proj
+ * (LIB/core/utils.hpp:22-27). */
+static v3 environment_of(const po_scene* s, v3 dir) {
+    if (s->environment_tex == PTB_NO_TEXTURE) return s->environment;
+    float u = atan2f(dir.z, dir.x) * 0.1591F + 0.5F, v = asinf(dir.y) * 0.3183F + 0.5F;
+    v4 c = tex_sample(s, s->environment_tex, u, v);
+    return mulv(V(c.x, c.y, c.z), s->environment);
+}
+
 /* core::renderer::trace, LIB/core/renderer.cpp:437-643 — recursive, as written. */
 static rgba_t trace_lib(const po_scene* s, uint32_t bounce, uint32_t bounce_count, ray r, rng_t* g) {
     rgba_t future = {{0, 0, 0}, 1}; /* fvec4::future */
     if (bounce == 0) return future;
     g->rays++;
     scene_hit h = scene_intersect(s, &r, NULL);
-    if (!(h.t >= 0)) { rgba_t e = {s->environment, s->transparent ? 0.0f : 1.0f}; return e; }
+    if (!(h.t >= 0)) { rgba_t e = {environment_of(s, r.d), s->transparent ? 0.0f : 1.0f}; return e; }
     attrs_t at = hit_attrs(s, &h);
     mat_t m = material_of(s, at.material, at.u, at.v);
     if (!is_approx(m.opacity, 1) && rnd(g) > m.opacity)
@@ -941,7 +952,7 @@ static rgba_t trace_app(const po_scene* s, uint32_t initial_bounce, ray cur, rng
         g->rays++;
         scene_hit h = scene_intersect(s, &cur, NULL);
         if (!(h.t >= 0)) {
-            acc = add(acc, mulv(thr, s->environment));
+            acc = add(acc, mulv(thr, environment_of(s, cur.d)));
             alpha = s->transparent ? 0.0f : 1.0f;
             break;
         }

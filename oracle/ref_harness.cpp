@@ -132,7 +132,11 @@ fvec4 trace_iter_app(const core::renderer& r, uint8_t initial_bounce, const geom
         tl_rays++;
         auto result = r.intersect(current_ray);
         if (!result.hit) {
-            accumulated_color += throughput * r.environment_factor; // worker.cpp:313 (no env texture path)
+            if (r.environment) // worker.cpp:308-311
+                accumulated_color += throughput * (fvec3(r.environment->sample(equirectangular_proj(current_ray.get_dir()))) *
+                                                   r.environment_factor);
+            else
+                accumulated_color += throughput * r.environment_factor; // worker.cpp:313
             alpha = r.transparent_background ? 0.0f : 1.0f;
             break;
         }
@@ -274,7 +278,11 @@ fvec4 trace_iter_lib(const core::renderer& r, uint8_t bounce_count, const geomet
         if (!result.hit) {
             if (primary)
                 alpha = r.transparent_background ? 0 : 1;
-            radiance += throughput * r.environment_factor;
+            if (r.environment) // renderer.cpp:446-448
+                radiance += throughput * (fvec3(r.environment->sample(equirectangular_proj(ray.get_dir()))) *
+                                          r.environment_factor);
+            else
+                radiance += throughput * r.environment_factor;
             break;
         }
         fvec3 albedo = result.material->get_albedo(result.tex_coord);
@@ -487,6 +495,7 @@ void* ref_scene_from_desc(const ptb_scene_desc* d) {
     s->r.environment_factor =
         fvec3(d->environment_factor[0], d->environment_factor[1], d->environment_factor[2]);
     s->r.transparent_background = d->transparent_background != 0;
+    if (d->environment_tex_plus1) s->r.environment = textures[d->environment_tex_plus1 - 1]; // renderer.hpp:28
     index_scene(*s);
     return s;
 }

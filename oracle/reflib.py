@@ -63,7 +63,7 @@ class SceneDesc(C.Structure):
                 ("textures", C.POINTER(TextureDesc)), ("n_textures", C.c_uint32),
                 ("camera", CameraDesc), ("sun", SunDesc),
                 ("environment_factor", C.c_float * 3), ("transparent_background", C.c_uint32),
-                ("kd_use_sah", C.c_uint32), ("kd_max_depth", C.c_uint32)]
+                ("kd_use_sah", C.c_uint32), ("kd_max_depth", C.c_uint32), ("environment_tex_plus1", C.c_uint32)]
 
 
 class Hit(C.Structure):
@@ -95,7 +95,8 @@ class FlatScene:
 
     def __init__(self, meshes, surfaces, instances, materials, camera, sun=None,
                  environment_factor=(1.0, 1.0, 1.0), transparent_background=False,
-                 kd_use_sah=True, kd_max_depth=25, textures=()):
+                 kd_use_sah=True, kd_max_depth=25, textures=(), environment_texture=None):
+        self.environment_texture = None if environment_texture is None else int(environment_texture)
         self.meshes = [
             {k: np.ascontiguousarray(m[k], dtype=np.uint32 if k == "indices" else np.float32)
              for k in ("positions", "normals", "tangents", "uvs", "indices")} for m in meshes]
@@ -173,6 +174,7 @@ class FlatScene:
         d.transparent_background = int(self.transparent_background)
         d.kd_use_sah = int(self.kd_use_sah)
         d.kd_max_depth = self.kd_max_depth
+        d.environment_tex_plus1 = 0 if self.environment_texture is None else self.environment_texture + 1
         keep += [md, sd, idesc, mat, tex, self]
         return d, keep
 

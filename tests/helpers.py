@@ -34,7 +34,38 @@ def make_flat(cls, parts):
     """cls: reflib.FlatScene or ptb.SceneDescription (same constructor)."""
     return cls(parts["meshes"], parts["surfaces"], parts["instances"], parts["materials"], parts["camera"],
                parts["sun"], parts["environment_factor"], parts["transparent_background"],
-               textures=parts.get("textures", ()))
+               textures=parts.get("textures", ()), environment_texture=parts.get("environment_texture"))
+
+
+def environment_scene_parts(procedural):
+    """A small heightfield under an equirectangular float environment map (renderer.hpp:28 `environment`): the camera
+    looks along the horizon, so about half of the primary rays and most bounce rays end in the map."""
+    mesh = procedural.heightfield_mesh(12, 2.0, 7)
+    h, w = 32, 64
+    v, u = np.mgrid[0:h, 0:w]
+    env = np.zeros((h, w, 3), np.float32)
+    env[..., 0] = 0.2 + 0.8 * u / (w - 1)
+    env[..., 1] = 0.1 + 0.9 * v / (h - 1)
+    env[..., 2] = 0.5
+    env[4:9, 40:48] = (6.0, 5.0, 3.0)  # a bright patch: an image-based light
+    mats = [dict(albedo=(0.75, 0.7, 0.6), opacity=1.0, roughness=0.6, metallic=0.1, emissive=(0, 0, 0), ior=1.33,
+                 shadow_catcher=0)]
+    cam = procedural.look_at((0.2, 1.1, 3.2), (0.0, 0.6, 0.0))
+    return dict(meshes=[mesh], surfaces=np.array([[0, 0]], np.uint32),
+                instances=[((0, 0, 0), np.eye(3, dtype=np.float32).ravel(), 0, 1)], materials=mats,
+                camera=(cam[0], cam[1], 0.9), sun=None, environment_factor=(0.9, 1.0, 1.1),
+                transparent_background=False, textures=[dict(pixels=env, srgb=False)], environment_texture=0)
+
+
+def block_mean_agreement(a, b, scale=5.0, rel=0.01):
+    """Two noisy renders of the same 64x48 image: do their means agree within the pooled standard error
+    (estimated from 8x8 blocks)?  → (ok, difference of the means, standard error)"""
+    def block_means(x):
+        return x.reshape(6, 8, 8, 8, 3).mean((1, 3)).reshape(-1, 3)
+    diff = block_means(a) - block_means(b)
+    se = diff.std(0) / np.sqrt(len(diff)) + 1e-4
+    ok = bool(np.all(np.abs(diff.mean(0)) < scale * se + rel * np.abs(b.mean((0, 1)))))
+    return ok, diff.mean(0), se
 
 
 def bits(a):

@@ -419,6 +419,24 @@ def test_image_statistics_against_live_reference_sun_scene(ptb, reflib):
             assert abs(st["rays"] / st["paths"] - r_rays / (64 * 48 * 256)) < 0.05
 
 
+@pytest.mark.parametrize("mode,ref_mode,depth", [(0, 0, 4), (1, 1, 6)])
+def test_environment_map_image_statistics(ptb, procedural, portlib, reflib, mode, ref_mode, depth):
+    """renderer.hpp:28 `environment`: a ray that hits nothing samples the equirectangular texture
+    (renderer.cpp:446-448, worker.cpp:308-311).  Against the reference library when it travelled (mode 0 = its
+    unmodified renderer::trace), else against the plain-C oracle; both are noisy → pooled standard error."""
+    parts = H.environment_scene_parts(procedural)
+    flat = H.make_flat(reflib.FlatScene, parts)
+    if reflib.available():
+        want, _, _, _ = reflib.RefScene.from_flat(flat).render_linear(64, 48, 256, depth, mode=ref_mode)
+    else:
+        want, _, _, _ = portlib.PortScene(flat).render_linear(64, 48, 256, depth, mode=mode, seed=9, threads=8)
+    with ptb.Scene.create(H.make_flat(ptb.SceneDescription, parts)) as s:
+        rgb, _, st = s.render_tile(64, 48, 1024, depth, seed=5, integrator=mode)
+    ok, diff, se = H.block_mean_agreement(rgb, want)
+    assert ok, (diff, se)
+    assert rgb[:8].reshape(-1, 3).std(0).max() > 0.02  # the map is in the picture
+
+
 def test_render_is_deterministic_and_tiles_compose(cornell):
     """Size-independent properties: same seed → identical image; a frame rendered as four tiles equals the
     full-frame render bit for bit (RNG is keyed by global pixel and sample); sample ranges chain."""

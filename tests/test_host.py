@@ -44,6 +44,11 @@ def test_invalid_descriptions_are_rejected(ptb, procedural):
     assert e.value.status == ptb.PTB_E_INVALID
     with pytest.raises(ptb.PtbError):
         ptb.set_option("no_such_option", 1)
+    d = procedural.heightfield_scene(4)
+    d.environment_texture = 3  # there is no texture 3
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.Scene.create(d)
+    assert e.value.status == ptb.PTB_E_INVALID and "environment" in str(e.value)
     with pytest.raises(ptb.PtbError) as e:
         ptb.load_gltf_description("/nonexistent/scene.gltf")
     assert e.value.status == ptb.PTB_E_IO

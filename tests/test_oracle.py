@@ -58,6 +58,27 @@ def test_port_textured_scene_image_statistics(portlib, reflib, name, mode):
     assert np.all(np.abs(zs) < 4.5), zs
 
 
+@pytest.mark.parametrize("mode,ref_mode,depth", [(0, 0, 4), (1, 1, 6)])
+def test_port_environment_map_against_reference(portlib, reflib, procedural, mode, ref_mode, depth):
+    """Rays that hit nothing sample the equirectangular environment texture (renderer.cpp:446-448 — mode 0 runs the
+    unmodified renderer::trace — and worker.cpp:308-311)."""
+    if not reflib.available():
+        pytest.skip("oracle/_ref not built")
+    parts = H.environment_scene_parts(procedural)
+    flat = H.make_flat(reflib.FlatScene, parts)
+    ref = reflib.RefScene.from_flat(flat)
+    port = portlib.PortScene(flat)
+    r_rgb, _, r_rays, _ = ref.render_linear(64, 48, 192, depth, mode=ref_mode)
+    p_rgb, _, p_rays, _ = port.render_linear(64, 48, 192, depth, mode=mode, seed=9, threads=4)
+    ok, diff, se = H.block_mean_agreement(p_rgb, r_rgb)
+    assert ok, (diff, se)
+    if r_rays:  # the unmodified renderer::trace (mode 0) is not instrumented
+        assert abs(p_rays - r_rays) / r_rays < 0.02
+    # the map is really in the picture: the sky half of the frame is not the flat environment_factor
+    sky = r_rgb[:8].reshape(-1, 3)
+    assert sky.std(0).max() > 0.02 and r_rgb.mean() > 0.3
+
+
 def test_port_heightfield(portlib, reflib, procedural):
     sc = procedural.heightfield_scene(40)
     # the fixture was minted with the camera of that day; hits do not depend on the camera
