@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 1
+#define PTB_ABI_VERSION 2
 
 typedef enum ptb_status {
     PTB_OK = 0,

@@ -17,7 +17,7 @@ def test_abi_exports_every_declared_symbol(ptb):
     for name in sorted(declared):
         assert hasattr(lib, name), f"libptb.so does not export {name}"
     assert declared == set(ptb.EXPORTS), declared ^ set(ptb.EXPORTS)
-    assert lib.ptb_abi_version() == 1
+    assert lib.ptb_abi_version() == 2  # 2: ptb_scene_desc.environment_tex_plus1, ptb_trace_rays_dev, ptb_shard_*_dev
 
 
 def test_struct_layouts_match_header(ptb):
