@@ -178,8 +178,10 @@ def run_reference(args):
     if rank != 0:
         return 0
     desc_name, full_w, full_h, spp, depth, integ = CONFIGS[args.config]
-    r = cpu_reference(args.config, args.n_grid, depth, integ, sample_seconds=args.cpu_seconds, steps=args.steps,
-                      warmup=min(args.warmup, 1))
+    # every step is a bounded sample; the whole run (steps + one warm-up) is kept to about 2.5 minutes of CPU time
+    wu = min(args.warmup, 1)
+    per_step = max(2.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + wu)))
+    r = cpu_reference(args.config, args.n_grid, depth, integ, sample_seconds=per_step, steps=args.steps, warmup=wu)
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
