@@ -17,7 +17,15 @@ def test_abi_exports_every_declared_symbol(ptb):
     for name in sorted(declared):
         assert hasattr(lib, name), f"libptb.so does not export {name}"
     assert declared == set(ptb.EXPORTS), declared ^ set(ptb.EXPORTS)
-    assert lib.ptb_abi_version() == 2  # 2: ptb_scene_desc.environment_tex_plus1, ptb_trace_rays_dev, ptb_shard_*_dev
+    want = int(re.search(r"#define\s+PTB_ABI_VERSION\s+(\d+)", header).group(1))
+    assert lib.ptb_abi_version() == want
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: __graft_entry__.build() must compile everything and exit cleanly."""
+    import __graft_entry__ as g
+    g.build()
+    assert g.abi_version_of_header() >= 2
 
 
 def test_struct_layouts_match_header(ptb):
