@@ -102,7 +102,31 @@ class TileReq(C.Structure):
     _fields_ = [("full_w", C.c_uint32), ("full_h", C.c_uint32), ("x0", C.c_uint32), ("y0", C.c_uint32),
                 ("w", C.c_uint32), ("h", C.c_uint32), ("spp", C.c_uint32), ("max_depth", C.c_uint32),
                 ("seed", C.c_uint64), ("first_sample", C.c_uint32), ("integrator", C.c_uint32),
-                ("first_sample_unjittered", C.c_uint32), ("reserved", C.c_uint32)]
+                ("first_sample_unjittered", C.c_uint32), ("reserved", C.c_uint32), ("claim_mask", C.c_void_p)]
+
+
+class FrameReq(C.Structure):
+    _fields_ = [("full_w", C.c_uint32), ("full_h", C.c_uint32), ("spp", C.c_uint32), ("max_depth", C.c_uint32),
+                ("seed", C.c_uint64), ("integrator", C.c_uint32), ("first_sample_unjittered", C.c_uint32),
+                ("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("tiles_in_flight", C.c_uint32),
+                ("output", C.c_uint32)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("n_tiles", C.c_uint32), ("n_ranks", C.c_uint32), ("gpu_seconds", C.c_double),
+                ("wall_seconds", C.c_double), ("tiles_per_rank", C.c_uint64 * 16),
+                ("gpu_seconds_per_rank", C.c_double * 16)]
+
+    def as_dict(self):
+        n = self.n_ranks
+        return dict(paths=self.paths, rays=self.rays, kernel_launches=self.kernel_launches, n_tiles=self.n_tiles,
+                    n_ranks=n, gpu_seconds=self.gpu_seconds, wall_seconds=self.wall_seconds,
+                    tiles_per_rank=list(self.tiles_per_rank[:n]),
+                    gpu_seconds_per_rank=list(self.gpu_seconds_per_rank[:n]))
+
+
+OUT_NONE, OUT_RGBA32F, OUT_RGBA8 = 0, 1, 2
 
 
 class RenderStats(C.Structure):
@@ -126,6 +150,10 @@ EXPORTS = [
     "ptb_write_png", "ptb_worker_run", "ptb_host_build_kd", "ptb_desc_load_gltf", "ptb_desc_get", "ptb_desc_free",
     "ptb_camera_rays", "ptb_trace_rays_stats", "ptb_extend_registers", "ptb_selftest_division", "ptb_set_option", "ptb_last_error",
     "ptb_abi_version", "ptb_device_count",
+    "ptb_scene_blob", "ptb_scene_export_header", "ptb_scene_import", "ptb_scene_clone",
+    "ptb_group_create", "ptb_group_destroy", "ptb_group_barrier", "ptb_group_render_frame",
+    "ptb_ctx_create", "ptb_ctx_destroy", "ptb_ctx_set_scene", "ptb_ctx_load_gltf", "ptb_ctx_scene", "ptb_render_frame",
+    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host",
 ]
 
 _lib = None
@@ -199,6 +227,43 @@ def lib():
     L.ptb_extend_registers.restype = C.c_int
     L.ptb_selftest_division.restype = C.c_uint64
     L.ptb_selftest_division.argtypes = [C.c_uint64, C.c_uint64]
+    L.ptb_scene_blob.restype = st
+    L.ptb_scene_blob.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.ptb_scene_export_header.restype = st
+    L.ptb_scene_export_header.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.ptb_scene_import.restype = st
+    L.ptb_scene_import.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.ptb_scene_clone.restype = st
+    L.ptb_scene_clone.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.ptb_group_create.restype = st
+    L.ptb_group_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.ptb_group_destroy.restype = None
+    L.ptb_group_destroy.argtypes = [C.c_void_p]
+    L.ptb_group_barrier.restype = st
+    L.ptb_group_barrier.argtypes = [C.c_void_p]
+    L.ptb_group_render_frame.restype = st
+    L.ptb_group_render_frame.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FrameReq), C.c_void_p, C.POINTER(FrameStats)]
+    L.ptb_ctx_create.restype = st
+    L.ptb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    L.ptb_ctx_destroy.restype = None
+    L.ptb_ctx_destroy.argtypes = [C.c_void_p]
+    L.ptb_ctx_set_scene.restype = st
+    L.ptb_ctx_set_scene.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
+    L.ptb_ctx_load_gltf.restype = st
+    L.ptb_ctx_load_gltf.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32]
+    L.ptb_ctx_scene.restype = C.c_void_p
+    L.ptb_ctx_scene.argtypes = [C.c_void_p, C.c_int]
+    L.ptb_render_frame.restype = st
+    L.ptb_render_frame.argtypes = [C.c_void_p, C.POINTER(FrameReq), C.c_void_p, C.POINTER(FrameStats)]
+    L.ptb_worker_run_ctx.restype = st
+    L.ptb_worker_run_ctx.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, u32p, u32p,
+                                     C.POINTER(FrameStats)]
+    L.ptb_host_alloc.restype = st
+    L.ptb_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+    L.ptb_host_free.restype = None
+    L.ptb_host_free.argtypes = [C.c_void_p]
+    L.ptb_group_selftest_host.restype = st
+    L.ptb_group_selftest_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     _lib = L
     return L
 
@@ -396,9 +461,10 @@ def host_build_kd(positions, indices, use_sah=True, max_depth=25, threads=0):
 class Scene:
     """A scene resident in HBM (ptb_scene)."""
 
-    def __init__(self, handle, keep=None):
+    def __init__(self, handle, keep=None, owned=True):
         self.h = handle
         self._keep = keep
+        self._owned = owned  # False: the handle belongs to a Context
 
     @classmethod
     def create(cls, desc: SceneDescription, device: int = 0) -> "Scene":
@@ -414,9 +480,37 @@ class Scene:
         return cls(h)
 
     def close(self):
-        if self.h:
+        if self.h and self._owned:
             lib().ptb_scene_destroy(self.h)
-            self.h = None
+        self.h = None
+
+    # -- replication: the flattened scene is one device allocation (blob) + a plain-data header
+    def blob(self):
+        """→ (device pointer, bytes) of the scene's single HBM allocation."""
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(lib().ptb_scene_blob(self.h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def export_header(self) -> bytes:
+        n = C.c_uint64()
+        _check(lib().ptb_scene_export_header(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(lib().ptb_scene_export_header(self.h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    @classmethod
+    def import_header(cls, header: bytes, device: int, src_blob: int = 0, src_device: int = 0) -> "Scene":
+        """A replica from a header; src_blob = 0 leaves the blob for the caller to fill (e.g. an NCCL broadcast)."""
+        h = C.c_void_p()
+        _check(lib().ptb_scene_import(header, len(header), device, C.c_void_p(src_blob) if src_blob else None,
+                                      src_device, C.byref(h)))
+        return cls(h)
+
+    def clone(self, device: int) -> "Scene":
+        """GPU → GPU copy of the flattened scene onto another device (no rebuild)."""
+        h = C.c_void_p()
+        _check(lib().ptb_scene_clone(self.h, device, C.byref(h)))
+        return Scene(h)
 
     def __del__(self):
         try:
@@ -470,32 +564,188 @@ class Scene:
         return od
 
     @staticmethod
-    def _req(full_w, full_h, spp, max_depth, tile, seed, integrator, first_sample, first_sample_unjittered):
+    def _req(full_w, full_h, spp, max_depth, tile, seed, integrator, first_sample, first_sample_unjittered,
+             claim_mask=0):
         x0, y0, w, h = tile if tile else (0, 0, full_w, full_h)
         return TileReq(full_w, full_h, x0, y0, w, h, spp, max_depth, seed, first_sample, integrator,
-                       int(first_sample_unjittered), 0)
+                       int(first_sample_unjittered), 0, claim_mask)
 
     def render_tile(self, full_w, full_h, spp, max_depth, tile=None, seed=1, integrator=INTEGRATOR_LIB,
-                    first_sample=0, first_sample_unjittered=False):
-        """→ (rgb[h,w,3] linear running mean, alpha[h,w], stats dict); host buffers, synchronous."""
+                    first_sample=0, first_sample_unjittered=False, state=None):
+        """→ (rgb[h,w,3] linear running mean, alpha[h,w], stats dict); host buffers, synchronous.
+
+        Sample ranges chain through caller-owned state: pass ``state=(rgb, alpha, claim_mask)`` as an earlier
+        call returned / filled them (claim_mask: uint8[h,w], only read for transparent-background scenes) together
+        with ``first_sample`` = the number of samples they hold; the arrays are updated in place."""
+        x0, y0, w, h = tile if tile else (0, 0, full_w, full_h)
+        if state is not None:
+            rgb, alpha, mask = state
+            assert rgb.dtype == np.float32 and rgb.shape == (h, w, 3) and rgb.flags.c_contiguous
+            assert alpha.dtype == np.float32 and alpha.shape == (h, w) and alpha.flags.c_contiguous
+            assert mask.dtype == np.uint8 and mask.shape == (h, w) and mask.flags.c_contiguous
+        else:
+            rgb = np.empty((h, w, 3), np.float32)
+            alpha = np.empty((h, w), np.float32)
+            mask = None
         req = self._req(full_w, full_h, spp, max_depth, tile, seed, integrator, first_sample,
-                        first_sample_unjittered)
-        rgb = np.empty((req.h, req.w, 3), np.float32)
-        alpha = np.empty((req.h, req.w), np.float32)
+                        first_sample_unjittered, mask.ctypes.data if mask is not None else 0)
         s = RenderStats()
         _check(lib().ptb_render_tile(self.h, C.byref(req), _fp(rgb), _fp(alpha), C.byref(s)))
         return rgb, alpha, s.as_dict()
 
     def render_tile_dev(self, rgba_dev_ptr: int, full_w, full_h, spp, max_depth, tile=None, seed=1,
                         integrator=INTEGRATOR_LIB, first_sample=0, first_sample_unjittered=False, stream=0,
-                        want_stats=True):
-        """Result stays in device memory (w*h float4 at rgba_dev_ptr); stream is a cudaStream_t value."""
+                        want_stats=True, claim_mask_dev: int = 0):
+        """Result stays in device memory (w*h float4 at rgba_dev_ptr, IN/OUT when first_sample != 0; claim_mask_dev:
+        w*h bytes of caller-owned device memory for transparent-background scenes); stream is a cudaStream_t value."""
         req = self._req(full_w, full_h, spp, max_depth, tile, seed, integrator, first_sample,
-                        first_sample_unjittered)
+                        first_sample_unjittered, claim_mask_dev)
         s = RenderStats()
         _check(lib().ptb_render_tile_dev(self.h, C.byref(req), C.c_void_p(rgba_dev_ptr), C.c_void_p(stream),
                                          C.byref(s) if want_stats else None))
         return s.as_dict() if want_stats else None
+
+
+def _frame_req(full_w, full_h, spp, max_depth, seed=1, integrator=INTEGRATOR_LIB, first_sample_unjittered=False,
+               tile=(0, 0), tiles_in_flight=0, output=OUT_RGBA32F) -> FrameReq:
+    return FrameReq(int(full_w), int(full_h), int(spp), int(max_depth), int(seed), int(integrator),
+                    int(bool(first_sample_unjittered)), int(tile[0]), int(tile[1]), int(tiles_in_flight), int(output))
+
+
+def _frame_out(req: FrameReq, out):
+    """→ (array, pointer) for the frame output of `req` (allocates pageable memory when `out` is None)."""
+    if req.output == OUT_NONE:
+        return None, None
+    shape, dtype = ((req.full_h, req.full_w, 4), np.float32 if req.output == OUT_RGBA32F else np.uint8)
+    if out is None:
+        out = np.empty(shape, dtype)
+    if isinstance(out, np.ndarray):
+        assert out.dtype == dtype and out.size == int(np.prod(shape)) and out.flags.c_contiguous
+        return out, C.c_void_p(out.ctypes.data)
+    return out, C.c_void_p(int(out))  # a raw host pointer (e.g. a pinned torch tensor's data_ptr())
+
+
+class PinnedBuffer:
+    """Pinned host memory from ptb_host_alloc, viewed as a numpy array (frame outputs without a staging copy)."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(lib().ptb_host_alloc(n, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)).view(self.dtype).reshape(self.shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib().ptb_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def group_selftest_host(name: str, rank: int, world: int, n_tiles: int, frames: int, work_us: int = 0) -> np.ndarray:
+    """Host-only run of the group's rendezvous / tile counter / barrier → uint8[frames, n_tiles], 1 = claimed here."""
+    mine = np.zeros((frames, n_tiles), np.uint8)
+    _check(lib().ptb_group_selftest_host(name.encode(), rank, world, n_tiles, frames, work_us, mine.ctypes.data))
+    return mine
+
+
+class Group:
+    """One rank (= one GPU, one process) of a tile-sharded frame renderer (ptb_group).  Every method is collective."""
+
+    def __init__(self, name: str, rank: int, world: int, device: int):
+        h = C.c_void_p()
+        _check(lib().ptb_group_create(name.encode(), rank, world, device, C.byref(h)))
+        self.h, self.rank, self.world, self.device = h, rank, world, device
+
+    def close(self):
+        if self.h:
+            lib().ptb_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def barrier(self):
+        _check(lib().ptb_group_barrier(self.h))
+
+    def render_frame(self, scene: "Scene", full_w, full_h, spp, max_depth, out=None, **kw):
+        """→ (frame or None, stats dict or None); the frame and the stats exist on rank 0 only."""
+        req = _frame_req(full_w, full_h, spp, max_depth, **kw)
+        arr, ptr = (None, None)
+        if self.rank == 0:
+            arr, ptr = _frame_out(req, out)
+        st = FrameStats()
+        _check(lib().ptb_group_render_frame(self.h, scene.h, C.byref(req), ptr, C.byref(st) if self.rank == 0 else None))
+        return arr, (st.as_dict() if self.rank == 0 else None)
+
+
+class Context:
+    """One process driving n GPUs with one host thread each (ptb_ctx): what replaces worker::run on a multi-GPU box."""
+
+    def __init__(self, n_gpus: int, devices=None):
+        h = C.c_void_p()
+        dv = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        _check(lib().ptb_ctx_create(n_gpus, dv, C.byref(h)))
+        self.h, self.n = h, n_gpus
+
+    def close(self):
+        if self.h:
+            lib().ptb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_scene(self, desc: "SceneDescription"):
+        d, keep = desc.to_c()
+        _check(lib().ptb_ctx_set_scene(self.h, C.byref(d)))
+
+    def load_gltf(self, path, camera_index=0, sun_light_index=0):
+        _check(lib().ptb_ctx_load_gltf(self.h, os.fsencode(path), camera_index, sun_light_index))
+
+    def scene(self, i: int = 0) -> "Scene":
+        """The replica on the context's i-th GPU (owned by the context)."""
+        p = lib().ptb_ctx_scene(self.h, i)
+        if not p:
+            raise PtbError(PTB_E_INVALID, "the context has no scene")
+        return Scene(C.c_void_p(p), owned=False)
+
+    def render_frame(self, full_w, full_h, spp, max_depth, out=None, **kw):
+        req = _frame_req(full_w, full_h, spp, max_depth, **kw)
+        arr, ptr = _frame_out(req, out)
+        st = FrameStats()
+        _check(lib().ptb_render_frame(self.h, C.byref(req), ptr, C.byref(st)))
+        return arr, st.as_dict()
+
+    def worker_run(self, worker_info, scene_dir, png_path=None):
+        """ptb_worker_run over all GPUs of the context → (rgba8[h,w,4], frame stats)."""
+        import json as _json
+        text = worker_info if isinstance(worker_info, str) else _json.dumps(worker_info)
+        try:
+            d = _json.loads(text)
+            w, h = int(float(d.get("X", 640))), int(float(d.get("Y", 480)))
+        except Exception:
+            w, h = 640, 480
+        out = np.empty((h, w, 4), np.uint8)
+        wo, ho, st = C.c_uint32(), C.c_uint32(), FrameStats()
+        _check(lib().ptb_worker_run_ctx(self.h, text.encode(), os.fsencode(scene_dir),
+                                        os.fsencode(png_path) if png_path else None, out.ctypes.data, C.byref(wo),
+                                        C.byref(ho), C.byref(st)))
+        assert (wo.value, ho.value) == (w, h)
+        return out, st.as_dict()
 
 
 def tonemap_rgba8(rgb, alpha=None) -> np.ndarray:

@@ -23,7 +23,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OUT = os.path.join(HERE, "libptb.so")
 OBJ = os.path.join(HERE, "build")
 
-CU_SOURCES = ["kernels.cu", "extend.cu", "extend_coop.cu", "extend_ctx.cu", "scene.cu", "render.cu", "api.cu"]
+CU_SOURCES = ["kernels.cu", "extend.cu", "extend_coop.cu", "extend_ctx.cu", "scene.cu", "render.cu", "frame.cu", "api.cu"]
 CXX_SOURCES = ["kd_build.cpp", "gltf.cpp", "png.cpp"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -87,7 +87,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             _run([cxx] + CXX_FLAGS + ["-I" + _cuda_include(), "-c", s, "-o", o], verbose)
         objs.append(o)
     if force or _stale(OUT, objs):
-        _run([nvcc, "-ccbin", cxx] + ARCH + ["-shared", "-o", OUT] + objs + ["-lz", "-lpthread", "-cudart", "static"],
+        _run([nvcc, "-ccbin", cxx] + ARCH + ["-shared", "-o", OUT] + objs + ["-lz", "-lpthread", "-lrt", "-cudart", "static"],
              verbose)
     return OUT
 

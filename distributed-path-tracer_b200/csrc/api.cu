@@ -11,6 +11,7 @@
 #include <functional>
 
 #include "errors.hpp"
+#include "frame.hpp"
 #include "json.hpp"
 #include "kd_build.hpp"
 #include "kernels.hpp"
@@ -88,6 +89,7 @@ ptb_status ptb_scene_dump_kd(const ptb_scene* scene, uint32_t mesh, uint32_t* wo
                              uint64_t* n_words) {
     return guarded([&] {
         if (!scene || !n_words) throw ptb::Error(PTB_E_INVALID, "scene or n_words is NULL");
+        if (scene->replica) throw ptb::Error(PTB_E_INVALID, "a replica holds no host copy of the trees; dump the built scene");
         if (mesh >= scene->trees.size()) throw ptb::Error(PTB_E_INVALID, "mesh out of range");
         std::vector<uint32_t> w;
         ptb::dump_kd_tree(scene->trees[mesh], w);
@@ -256,6 +258,15 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
             ptb::g_options.extend_tests = value;
         } else if (n == "time_stages") {
             ptb::g_options.time_stages = value ? 1 : 0;
+        } else if (n == "group_timeout_ms") {
+            if (value < 100) throw ptb::Error(PTB_E_INVALID, "group_timeout_ms must be >= 100");
+            ptb::g_options.group_timeout_ms = value;
+        } else if (n == "frame_tiles_in_flight") {
+            if (value < 1 || value > 16) throw ptb::Error(PTB_E_INVALID, "frame_tiles_in_flight must be 1..16");
+            ptb::g_options.frame_tiles_in_flight = value;
+        } else if (n == "frame_queue_depth") {
+            if (value < 1 || value > 2) throw ptb::Error(PTB_E_INVALID, "frame_queue_depth must be 1 or 2");
+            ptb::g_options.frame_queue_depth = value;
         } else if (n == "extend_blocks_per_sm") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_blocks_per_sm out of range");
             ptb::g_options.extend_blocks_per_sm = value;
@@ -292,49 +303,67 @@ const int g_env_options_applied = [] {
 }();
 } // namespace
 
+} // extern "C"
+
 // The Lambda worker's entry (my_handler → worker::run, APP/main.cpp:9-31, APP/processors/worker/worker.cpp:25-105)
 // without the S3 hops: the request is the worker_info JSON the preprocessor sends, the scene is read from a local
 // mirror of s3://scene_bucket/scene_root.
+namespace {
+
+struct WorkerRequest {
+    ptb::OwnedScene owned;
+    uint32_t samples = 50, bounces = 10, X = 640, Y = 480;
+    uint64_t seed = 0;
+};
+
+void parse_worker_request(const char* worker_info_json, const char* scene_dir, WorkerRequest& out) {
+    if (!worker_info_json || !scene_dir) throw ptb::Error(PTB_E_INVALID, "worker_info_json or scene_dir is NULL");
+    ptb::Json info;
+    try {
+        const std::string text(worker_info_json);
+        info = ptb::JsonParser(text).parse();
+    } catch (const std::exception& e) {
+        throw ptb::Error(PTB_E_INVALID, std::string("worker_info: ") + e.what());
+    }
+    if (info.kind != ptb::Json::Object) throw ptb::Error(PTB_E_INVALID, "worker_info: not a JSON object");
+    // models::worker_info (APP/models/work_info.hpp:17-31); the preprocessor omits samples/bounces/X/Y
+    // (PRE/app.py:119-127), in which case the worker's own defaults apply (worker.hpp:20-24)
+    ptb::WorkFilter work;
+    if (const ptb::Json* si = info.find("scene_info"))
+        if (const ptb::Json* w = si->find("work"))
+            for (const auto& kv : w->obj) {
+                std::vector<int>& v = work[kv.first];
+                for (const ptb::Json& p : kv.second.arr) v.push_back(static_cast<int>(p.number(-1)));
+            }
+    out.samples = static_cast<uint32_t>(info.get("samples", 50.0));
+    out.bounces = static_cast<uint32_t>(info.get("bounces", 10.0));
+    out.X = static_cast<uint32_t>(static_cast<float>(info.get("X", 640.0)));
+    out.Y = static_cast<uint32_t>(static_cast<float>(info.get("Y", 480.0)));
+    if (!out.X || !out.Y || out.bounces > 255) throw ptb::Error(PTB_E_INVALID, "worker_info: bad X / Y / bounces");
+    out.seed = std::hash<std::string>{}(info.get("worker_id", std::string("0")));
+    const std::string gltf = std::string(scene_dir) + "/scene.gltf"; // worker::download_gltf_file: scene_root + "scene.gltf"
+    if (!std::ifstream(gltf).good()) throw ptb::Error(PTB_E_IO, "cannot open " + gltf);
+    ptb::load_gltf(gltf, 0, 0, out.owned, info.has("scene_info") ? &work : nullptr);
+}
+
+} // namespace
+
+extern "C" {
+
 ptb_status ptb_worker_run(const char* worker_info_json, const char* scene_dir, int device, const char* png_path,
                           uint8_t* rgba8_out, uint32_t* width_out, uint32_t* height_out, ptb_render_stats* stats_out) {
     return guarded([&] {
-        if (!worker_info_json || !scene_dir) throw ptb::Error(PTB_E_INVALID, "worker_info_json or scene_dir is NULL");
-        ptb::Json info;
-        try {
-            const std::string text(worker_info_json);
-            info = ptb::JsonParser(text).parse();
-        } catch (const std::exception& e) {
-            throw ptb::Error(PTB_E_INVALID, std::string("worker_info: ") + e.what());
-        }
-        if (info.kind != ptb::Json::Object) throw ptb::Error(PTB_E_INVALID, "worker_info: not a JSON object");
-        // models::worker_info (APP/models/work_info.hpp:17-31); the preprocessor omits samples/bounces/X/Y
-        // (PRE/app.py:119-127), in which case the worker's own defaults apply (worker.hpp:20-24)
-        ptb::WorkFilter work;
-        if (const ptb::Json* si = info.find("scene_info"))
-            if (const ptb::Json* w = si->find("work"))
-                for (const auto& kv : w->obj) {
-                    std::vector<int>& v = work[kv.first];
-                    for (const ptb::Json& p : kv.second.arr) v.push_back(static_cast<int>(p.number(-1)));
-                }
-        const uint32_t samples = static_cast<uint32_t>(info.get("samples", 50.0));
-        const uint32_t bounces = static_cast<uint32_t>(info.get("bounces", 10.0));
-        const uint32_t X = static_cast<uint32_t>(static_cast<float>(info.get("X", 640.0)));
-        const uint32_t Y = static_cast<uint32_t>(static_cast<float>(info.get("Y", 480.0)));
-        if (!X || !Y || bounces > 255) throw ptb::Error(PTB_E_INVALID, "worker_info: bad X / Y / bounces");
-        const std::string worker_id = info.get("worker_id", std::string("0"));
-
-        std::string gltf = std::string(scene_dir) + "/scene.gltf"; // worker::download_gltf_file: scene_root + "scene.gltf"
-        if (!std::ifstream(gltf).good()) throw ptb::Error(PTB_E_IO, "cannot open " + gltf);
-        ptb::OwnedScene owned;
-        ptb::load_gltf(gltf, 0, 0, owned, info.has("scene_info") ? &work : nullptr);
-        ptb_scene* scene = ptb::create_scene(owned.view(), device);
+        WorkerRequest wr;
+        parse_worker_request(worker_info_json, scene_dir, wr);
+        const uint32_t X = wr.X, Y = wr.Y;
+        ptb_scene* scene = ptb::create_scene(wr.owned.view(), device);
         try {
             ptb_tile_req req{};
             req.full_w = req.w = X;
             req.full_h = req.h = Y;
-            req.spp = samples;
-            req.max_depth = bounces;
-            req.seed = std::hash<std::string>{}(worker_id);
+            req.spp = wr.samples;
+            req.max_depth = wr.bounces;
+            req.seed = wr.seed;
             req.integrator = PTB_INTEGRATOR_APP_RR;
             req.first_sample_unjittered = 1; // worker::generate_rays, worker.cpp:125-129
             std::vector<float> rgb(size_t(X) * Y * 3), alpha(size_t(X) * Y);
@@ -351,6 +380,154 @@ ptb_status ptb_worker_run(const char* worker_info_json, const char* scene_dir, i
         }
         ptb::destroy_scene(scene);
     });
+}
+
+// worker::run on every GPU of the box: same request, the frame tile-sharded over the context's GPUs.
+ptb_status ptb_worker_run_ctx(ptb_ctx* ctx, const char* worker_info_json, const char* scene_dir, const char* png_path,
+                              uint8_t* rgba8_out, uint32_t* width_out, uint32_t* height_out, ptb_frame_stats* stats_out) {
+    return guarded([&] {
+        if (!ctx) throw ptb::Error(PTB_E_INVALID, "ctx is NULL");
+        WorkerRequest wr;
+        parse_worker_request(worker_info_json, scene_dir, wr);
+        ptb::ctx_set_scene(ctx, wr.owned.view());
+        ptb_frame_req fr{};
+        fr.full_w = wr.X;
+        fr.full_h = wr.Y;
+        fr.spp = wr.samples;
+        fr.max_depth = wr.bounces;
+        fr.seed = wr.seed;
+        fr.integrator = PTB_INTEGRATOR_APP_RR;
+        fr.first_sample_unjittered = 1;
+        fr.output = PTB_OUT_RGBA8; // worker::generate_final_image's tonemap + encode, on rank 0's GPU
+        std::vector<uint8_t> rgba8(size_t(wr.X) * wr.Y * 4);
+        ptb::ctx_render_frame(ctx, fr, rgba8.data(), stats_out);
+        if (png_path) ptb::write_png_rgba8(png_path, rgba8.data(), wr.X, wr.Y);
+        if (rgba8_out) std::memcpy(rgba8_out, rgba8.data(), rgba8.size());
+        if (width_out) *width_out = wr.X;
+        if (height_out) *height_out = wr.Y;
+    });
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------------------------------
+
+ptb_status ptb_scene_blob(const ptb_scene* scene, void** blob_dev, uint64_t* blob_bytes) {
+    return guarded([&] {
+        if (!scene || !blob_dev || !blob_bytes) throw ptb::Error(PTB_E_INVALID, "NULL argument");
+        *blob_dev = scene->blob;
+        *blob_bytes = scene->blob_bytes;
+    });
+}
+
+ptb_status ptb_scene_export_header(const ptb_scene* scene, void* header, uint64_t capacity, uint64_t* n_bytes) {
+    return guarded([&] {
+        if (!scene || !n_bytes) throw ptb::Error(PTB_E_INVALID, "scene or n_bytes is NULL");
+        *n_bytes = ptb::scene_header_bytes();
+        if (header) {
+            if (capacity < *n_bytes) throw ptb::Error(PTB_E_INVALID, "capacity too small");
+            ptb::export_scene_header(scene, header);
+        }
+    });
+}
+
+ptb_status ptb_scene_import(const void* header, uint64_t n_bytes, int device, const void* src_blob_dev, int src_device,
+                            ptb_scene** out) {
+    return guarded([&] {
+        if (!out) throw ptb::Error(PTB_E_INVALID, "out is NULL");
+        *out = nullptr;
+        *out = ptb::import_scene(header, n_bytes, device, src_blob_dev, src_device);
+    });
+}
+
+ptb_status ptb_scene_clone(const ptb_scene* scene, int device, ptb_scene** out) {
+    return guarded([&] {
+        if (!out) throw ptb::Error(PTB_E_INVALID, "out is NULL");
+        *out = nullptr;
+        *out = ptb::clone_scene(scene, device);
+    });
+}
+
+ptb_status ptb_group_create(const char* name, int rank, int world, int device, ptb_group** out) {
+    return guarded([&] {
+        if (!out) throw ptb::Error(PTB_E_INVALID, "out is NULL");
+        *out = nullptr;
+        *out = ptb::group_create_processes(name, rank, world, device);
+    });
+}
+
+void ptb_group_destroy(ptb_group* group) {
+    try {
+        ptb::group_destroy(group);
+    } catch (...) {
+    }
+}
+
+ptb_status ptb_group_selftest_host(const char* name, int rank, int world, uint32_t n_tiles, uint32_t frames,
+                                   uint32_t work_us, uint8_t* mine_out) {
+    return guarded([&] { ptb::group_selftest_host(name, rank, world, n_tiles, frames, work_us, mine_out); });
+}
+
+ptb_status ptb_group_barrier(ptb_group* group) {
+    return guarded([&] { ptb::group_barrier_public(group); });
+}
+
+ptb_status ptb_group_render_frame(ptb_group* group, const ptb_scene* scene, const ptb_frame_req* req, void* out_host,
+                                  ptb_frame_stats* stats_out) {
+    return guarded([&] {
+        if (!req) throw ptb::Error(PTB_E_INVALID, "req is NULL");
+        ptb::group_render_frame(group, scene, *req, out_host, stats_out);
+    });
+}
+
+ptb_status ptb_ctx_create(int n_gpus, const int* devices, ptb_ctx** out) {
+    return guarded([&] {
+        if (!out) throw ptb::Error(PTB_E_INVALID, "out is NULL");
+        *out = nullptr;
+        *out = ptb::ctx_create(n_gpus, devices);
+    });
+}
+
+void ptb_ctx_destroy(ptb_ctx* ctx) {
+    try {
+        ptb::ctx_destroy(ctx);
+    } catch (...) {
+    }
+}
+
+ptb_status ptb_ctx_set_scene(ptb_ctx* ctx, const ptb_scene_desc* desc) {
+    return guarded([&] {
+        if (!desc) throw ptb::Error(PTB_E_INVALID, "desc is NULL");
+        ptb::ctx_set_scene(ctx, *desc);
+    });
+}
+
+ptb_status ptb_ctx_load_gltf(ptb_ctx* ctx, const char* path, uint32_t camera_index, uint32_t sun_light_index) {
+    return guarded([&] {
+        if (!path) throw ptb::Error(PTB_E_INVALID, "path is NULL");
+        ptb::OwnedScene owned;
+        ptb::load_gltf(path, camera_index, sun_light_index, owned);
+        ptb::ctx_set_scene(ctx, owned.view());
+    });
+}
+
+const ptb_scene* ptb_ctx_scene(const ptb_ctx* ctx, int i) { return ptb::ctx_scene(ctx, i); }
+
+ptb_status ptb_render_frame(ptb_ctx* ctx, const ptb_frame_req* req, void* out_host, ptb_frame_stats* stats_out) {
+    return guarded([&] {
+        if (!req) throw ptb::Error(PTB_E_INVALID, "req is NULL");
+        ptb::ctx_render_frame(ctx, *req, out_host, stats_out);
+    });
+}
+
+ptb_status ptb_host_alloc(uint64_t bytes, void** out) {
+    return guarded([&] {
+        if (!out) throw ptb::Error(PTB_E_INVALID, "out is NULL");
+        *out = nullptr;
+        PTB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    });
+}
+
+void ptb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 const char* ptb_last_error(void) { return tl_error.c_str(); }

@@ -395,16 +395,20 @@ __global__ void __launch_bounds__(SHADE_THREADS)
 // ---------------------------------------------------------- accumulate -----
 
 // The reference blends sample after sample, in order (renderer.cpp:373-399):
-// `sample` is the global sample index, so waves can be chained.
+// `sample` is the global sample index, so waves can be chained.  The destination is addressed with a row
+// pitch, so a tile can be accumulated in place inside a full frame — which may live in ANOTHER GPU's memory
+// (peer-mapped over NVLink): the tile return of the multi-GPU frame is this kernel's store, not a collective
+// that follows it.  `fresh`: this wave starts the running mean (nothing is read from dst / claimed).
 __global__ void __launch_bounds__(256)
-    accumulate_kernel(WaveGeom g, const float4* __restrict__ sample_out, float4* __restrict__ accum,
-                      uint8_t* __restrict__ claimed, bool transparent) {
+    accumulate_kernel(WaveGeom g, const float4* __restrict__ sample_out, float4* __restrict__ dst, uint32_t pitch,
+                      uint8_t* __restrict__ claimed, bool transparent, bool fresh) {
     const uint32_t npix = g.w * g.h;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         const uint32_t x = i % g.w, y = i / g.w;
         const uint32_t q = pixel_to_slot(g, x, y);
-        float4 px = accum[i];
-        bool cl = transparent ? (claimed[i] != 0) : false;
+        float4* out = dst + size_t(y) * pitch + x;
+        float4 px = fresh ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : *out;
+        bool cl = (transparent && !fresh) ? (claimed[i] != 0) : false;
         for (uint32_t s = 0; s < g.wave_samples; s++) {
             const float4 d = __ldcs(sample_out + sample_slot_to_path(g, s, q));
             const uint32_t sample = g.first_sample + s;
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(256)
             px.z = (px.z * fs + d.z) / fs1;
             px.w = (px.w * fs + d.w) / fs1;
         }
-        accum[i] = px;
+        *out = px;
         if (transparent) claimed[i] = cl ? 1 : 0;
     }
 }
@@ -462,6 +466,25 @@ __global__ void split_rgba_kernel(const float4* __restrict__ rgba, uint64_t n, f
         rgb[3 * i + 1] = v.y;
         rgb[3 * i + 2] = v.z;
         if (alpha) alpha[i] = v.w;
+    }
+}
+
+__global__ void join_rgba_kernel(const float* __restrict__ rgb, const float* __restrict__ alpha, uint64_t n,
+                                 float4* __restrict__ rgba) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        rgba[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], alpha ? alpha[i] : 1.0f);
+}
+
+// frame → RGBA8 in one pass (tonemap_approx_aces + image::write's encode, as tonemap_kernel)
+__global__ void tonemap_rgba_kernel(const float4* __restrict__ rgba, uint64_t n, uint8_t* __restrict__ rgba8) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 v = rgba[i];
+        uchar4 o;
+        o.x = (unsigned char)(powf(aces(v.x), 1 / 2.2F) * 255 + 0.5F);
+        o.y = (unsigned char)(powf(aces(v.y), 1 / 2.2F) * 255 + 0.5F);
+        o.z = (unsigned char)(powf(aces(v.z), 1 / 2.2F) * 255 + 0.5F);
+        o.w = (unsigned char)(v.w * 255 + 0.5F);
+        reinterpret_cast<uchar4*>(rgba8)[i] = o;
     }
 }
 
@@ -579,10 +602,10 @@ void launch_shade(const DScene& S, const WaveGeom& g, const RenderParams& rp, co
     }
 }
 
-void launch_accumulate(const WaveGeom& g, const float4* sample_out, float4* accum, uint8_t* claimed, bool transparent,
-                       cudaStream_t st) {
+void launch_accumulate(const WaveGeom& g, const float4* sample_out, float4* dst, uint32_t pitch, uint8_t* claimed,
+                       bool transparent, bool fresh, cudaStream_t st) {
     const uint64_t n = uint64_t(g.w) * g.h;
-    accumulate_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(g, sample_out, accum, claimed, transparent);
+    accumulate_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(g, sample_out, dst, pitch, claimed, transparent, fresh);
 }
 
 void launch_tonemap(const float* rgb, const float* alpha, uint64_t n, uint8_t* rgba8, cudaStream_t st) {
@@ -591,6 +614,14 @@ void launch_tonemap(const float* rgb, const float* alpha, uint64_t n, uint8_t* r
 
 void launch_split_rgba(const float4* rgba, uint64_t n, float* rgb, float* alpha, cudaStream_t st) {
     split_rgba_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(rgba, n, rgb, alpha);
+}
+
+void launch_join_rgba(const float* rgb, const float* alpha, uint64_t n, float4* rgba, cudaStream_t st) {
+    join_rgba_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(rgb, alpha, n, rgba);
+}
+
+void launch_tonemap_rgba(const float4* rgba, uint64_t n, uint8_t* rgba8, cudaStream_t st) {
+    tonemap_rgba_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(rgba, n, rgba8);
 }
 
 void launch_prep_rays(const float* origin_dir, uint64_t n, float4* ray_o, float4* ray_d, cudaStream_t st) {

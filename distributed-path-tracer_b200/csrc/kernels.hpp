@@ -68,10 +68,14 @@ void launch_extend(const DScene& S, const float4* ray_o, const float4* ray_d, ui
 void launch_shade(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& in,
                   const uint4* hits, const PathBuffers& out, float4* sample_out, const uint32_t* n_ptr,
                   uint32_t* n_next, DeviceCounters* counters, const LaunchCfg& cfg, cudaStream_t st);
-void launch_accumulate(const WaveGeom& g, const float4* sample_out, float4* accum, uint8_t* claimed,
-                       bool transparent, cudaStream_t st);
+// dst: the tile's pixel (0,0) inside a buffer with `pitch` pixels per row (own or peer-mapped memory);
+// fresh: this wave starts the running mean (dst / claimed are not read)
+void launch_accumulate(const WaveGeom& g, const float4* sample_out, float4* dst, uint32_t pitch, uint8_t* claimed,
+                       bool transparent, bool fresh, cudaStream_t st);
 void launch_tonemap(const float* rgb, const float* alpha, uint64_t n, uint8_t* rgba8, cudaStream_t st);
 void launch_split_rgba(const float4* rgba, uint64_t n, float* rgb, float* alpha, cudaStream_t st);
+void launch_join_rgba(const float* rgb, const float* alpha, uint64_t n, float4* rgba, cudaStream_t st);
+void launch_tonemap_rgba(const float4* rgba, uint64_t n, uint8_t* rgba8, cudaStream_t st);
 
 // explicit ray sets (ptb_trace_rays): normalise directions like geometry::ray's constructor, then export
 void launch_prep_rays(const float* origin_dir, uint64_t n, float4* ray_o, float4* ray_d, cudaStream_t st);

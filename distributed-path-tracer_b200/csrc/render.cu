@@ -56,6 +56,7 @@ struct Workspace {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> stage_ev; // pool for per-launch timing (option time_stages)
     std::mutex lock;
+    uint64_t launches = 0, paths = 0;  // since the last stream_counters_reset (frame driver)
     cudaEvent_t stage_event(size_t i) {
         while (stage_ev.size() <= i) {
             cudaEvent_t e;
@@ -113,19 +114,20 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     return c;
 }
 
-} // namespace
+struct TileTarget {
+    float4* base;
+    uint32_t pitch;   // pixels per row of the destination
+    uint8_t* claimed; // caller-owned claim mask (w*h bytes) or null
+};
 
-void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_dev, cudaStream_t st,
-                     ptb_render_stats* stats) {
-    if (!s || !rgba_dev) throw Error(PTB_E_INVALID, "scene or output is NULL");
-    if (req.w == 0 || req.h == 0 || req.full_w == 0 || req.full_h == 0) throw Error(PTB_E_INVALID, "empty tile or frame");
-    if (uint64_t(req.x0) + req.w > req.full_w || uint64_t(req.y0) + req.h > req.full_h)
-        throw Error(PTB_E_INVALID, "tile exceeds the frame");
-    if (req.max_depth > 255) throw Error(PTB_E_INVALID, "max_depth above 255 (the reference's bounce_count is uint8_t)");
-    if (req.integrator > 1) throw Error(PTB_E_INVALID, "unknown integrator");
-    PTB_CUDA(cudaSetDevice(s->device));
-    Workspace& w = workspace(s->device, st);
-    std::lock_guard<std::mutex> guard(w.lock);
+// The wavefront loop for one tile.  The caller holds w.lock.
+//   dst        where the running mean lives: pixel (0,0) of the tile inside a buffer with dst.pitch pixels per
+//              row (the caller's tile buffer, or a full frame — possibly peer-mapped memory of another GPU)
+//   dst.claimed  transparent-background claim mask of the tile (w*h bytes) or null → workspace scratch
+//   stats      non-null: counters are reset, the stream is synchronised at the end and the totals returned;
+//              null: nothing is reset or read (the frame driver reads the workspace's counters once per frame)
+void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& req, const TileTarget& dst, cudaStream_t st,
+                        ptb_render_stats* stats) {
     w.events();
 
     WaveGeom g{};
@@ -157,9 +159,20 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
     const uint32_t n_iters_fixed = req.max_depth;
     const size_t n_counters = size_t(n_iters_fixed) + MAX_EXTRA_ITERS + 2;
     w.qcount.ensure(n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t));
-    w.counters.ensure(sizeof(DeviceCounters));
+    if (!w.counters.p) {
+        w.counters.ensure(sizeof(DeviceCounters));
+        PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
+    }
     const bool transparent = s->d.transparent_background != 0;
-    if (transparent) w.claimed.ensure(size_t(req.w) * req.h);
+    uint8_t* claimed = dst.claimed;
+    if (transparent && !claimed) {
+        // scratch: enough for a call that starts its own running mean; chained calls must own the mask
+        if (req.first_sample != 0)
+            throw Error(PTB_E_INVALID, "first_sample != 0 on a transparent-background scene needs ptb_tile_req.claim_mask "
+                                       "(the state that chains sample ranges is caller-owned)");
+        w.claimed.ensure(size_t(req.w) * req.h);
+        claimed = (uint8_t*)w.claimed.p;
+    }
 
     uint32_t* qcount = (uint32_t*)w.qcount.p;
     uint32_t* qhead = qcount + n_counters;
@@ -170,12 +183,8 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
     // opacity or shadow-catcher pass-through.
     const bool may_pass_through = s->has_pass_through;
 
-    PTB_CUDA(cudaMemsetAsync(counters, 0, sizeof(DeviceCounters), st));
-    if (req.first_sample == 0) {
-        PTB_CUDA(cudaMemsetAsync(rgba_dev, 0, size_t(req.w) * req.h * sizeof(float4), st));
-        if (transparent) PTB_CUDA(cudaMemsetAsync(w.claimed.p, 0, size_t(req.w) * req.h, st));
-    }
-    PTB_CUDA(cudaEventRecord(w.ev[0], st));
+    if (stats) PTB_CUDA(cudaMemsetAsync(counters, 0, sizeof(DeviceCounters), st));
+    if (stats) PTB_CUDA(cudaEventRecord(w.ev[0], st));
 
     uint64_t launches = 0, extend_launches = 0, paths = 0;
     const bool time_stages = g_options.time_stages != 0 && stats != nullptr;
@@ -190,6 +199,9 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
         if (!time_stages) return;
         PTB_CUDA(cudaEventRecord(w.stage_event(n_stage_ev++), st));
     };
+    if (req.spp == 0 && req.first_sample == 0) { // renderer::render with sample_count 0 leaves the cleared image
+        PTB_CUDA(cudaMemset2DAsync(dst.base, size_t(dst.pitch) * sizeof(float4), 0, size_t(req.w) * sizeof(float4), req.h, st));
+    }
     for (uint32_t s0 = 0; s0 < req.spp; s0 += (uint32_t)wave_samples) {
         g.wave_samples = (uint32_t)std::min<uint64_t>(wave_samples, req.spp - s0);
         g.first_sample = req.first_sample + s0;
@@ -236,14 +248,19 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
             }
         }
         stage_begin(1);
-        launch_accumulate(g, (const float4*)w.sample_out.p, rgba_dev, (uint8_t*)w.claimed.p, transparent, st);
+        // the wave that starts the running mean writes without reading: a one-wave tile goes to its
+        // destination (the frame, possibly on another GPU) with this single store per pixel
+        launch_accumulate(g, (const float4*)w.sample_out.p, dst.base, dst.pitch, claimed, transparent,
+                          g.first_sample == 0, st);
         stage_end();
         launches++;
     }
-    PTB_CUDA(cudaEventRecord(w.ev[1], st));
+    w.launches += launches;
+    w.paths += paths;
     PTB_CUDA(cudaGetLastError());
 
     if (stats) {
+        PTB_CUDA(cudaEventRecord(w.ev[1], st));
         DeviceCounters hc{};
         PTB_CUDA(cudaMemcpyAsync(&hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
         PTB_CUDA(cudaStreamSynchronize(st));
@@ -269,24 +286,101 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
     }
 }
 
+void check_tile_req(const ptb_scene* s, const ptb_tile_req& req) {
+    if (!s) throw Error(PTB_E_INVALID, "scene is NULL");
+    if (req.w == 0 || req.h == 0 || req.full_w == 0 || req.full_h == 0) throw Error(PTB_E_INVALID, "empty tile or frame");
+    if (uint64_t(req.x0) + req.w > req.full_w || uint64_t(req.y0) + req.h > req.full_h)
+        throw Error(PTB_E_INVALID, "tile exceeds the frame");
+    if (req.max_depth > 255) throw Error(PTB_E_INVALID, "max_depth above 255 (the reference's bounce_count is uint8_t)");
+    if (req.integrator > 1) throw Error(PTB_E_INVALID, "unknown integrator");
+    if (uint64_t(req.first_sample) + req.spp >= (1ull << 32)) throw Error(PTB_E_INVALID, "sample index overflow");
+}
+
+} // namespace
+
+// ---- entry points used by the frame driver (frame.cu) -----------------------------------------------------------
+
+void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, float4* base, uint32_t pitch, cudaStream_t st) {
+    check_tile_req(s, req);
+    if (!base) throw Error(PTB_E_INVALID, "destination is NULL");
+    Workspace& w = workspace(s->device, st);
+    std::lock_guard<std::mutex> guard(w.lock);
+    render_tile_locked(w, s, req, TileTarget{base, pitch, nullptr}, st, nullptr);
+}
+
+void stream_counters_reset(int device, cudaStream_t st) {
+    Workspace& w = workspace(device, st);
+    std::lock_guard<std::mutex> guard(w.lock);
+    w.counters.ensure(sizeof(DeviceCounters));
+    PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
+    w.launches = w.paths = 0;
+}
+
+void stream_counters_read(int device, cudaStream_t st, uint64_t* rays, uint64_t* paths, uint64_t* launches) {
+    Workspace& w = workspace(device, st);
+    std::lock_guard<std::mutex> guard(w.lock);
+    DeviceCounters hc{};
+    if (w.counters.p) {
+        PTB_CUDA(cudaMemcpyAsync(&hc, w.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        PTB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (hc.bound_errors)
+        throw Error(PTB_E_CUDA, "instrumented extend kernel: " + std::to_string(hc.bound_errors) +
+                                    " index / stack bound violations");
+    *rays = hc.rays;
+    *paths = w.paths;
+    *launches = w.launches;
+}
+
+// ---- C ABI entry points ---------------------------------------------------------------------------------------
+
+void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_dev, cudaStream_t st,
+                     ptb_render_stats* stats) {
+    check_tile_req(s, req);
+    if (!rgba_dev) throw Error(PTB_E_INVALID, "output is NULL");
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device, st);
+    std::lock_guard<std::mutex> guard(w.lock);
+    // the running mean (rgba_dev) and the claim mask (req.claim_mask) are the caller's: nothing that chains
+    // sample ranges lives in the library
+    render_tile_locked(w, s, req, TileTarget{rgba_dev, req.w, static_cast<uint8_t*>(req.claim_mask)}, st, stats);
+}
+
 void render_tile_host(const ptb_scene* s, const ptb_tile_req& req, float* rgb_out, float* alpha_out,
                       ptb_render_stats* stats) {
-    if (!s || !rgb_out) throw Error(PTB_E_INVALID, "scene or output is NULL");
+    check_tile_req(s, req);
+    if (!rgb_out) throw Error(PTB_E_INVALID, "output is NULL");
     PTB_CUDA(cudaSetDevice(s->device));
-    Workspace& w = workspace(s->device);
-    const size_t npix = size_t(req.w) * req.h;
-    {
-        std::lock_guard<std::mutex> guard(w.lock);
-        w.accum.ensure(std::max<size_t>(npix, 1) * sizeof(float4));
-        w.io_a.ensure(std::max<size_t>(npix, 1) * 3 * sizeof(float));
-        w.io_b.ensure(std::max<size_t>(npix, 1) * sizeof(float));
-    }
     cudaStream_t st = nullptr;
-    render_tile_dev(s, req, (float4*)w.accum.p, st, stats);
+    Workspace& w = workspace(s->device, st);
+    // ONE lock from the first allocation to the last copy: two host threads on the same device share this
+    // workspace and must not free / overwrite each other's buffers
     std::lock_guard<std::mutex> guard(w.lock);
+    const size_t npix = size_t(req.w) * req.h;
+    const bool transparent = s->d.transparent_background != 0;
+    const bool chained = req.first_sample != 0;
+    if (chained && !alpha_out) throw Error(PTB_E_INVALID, "first_sample != 0 needs alpha_out (the running mean is in/out)");
+    if (chained && transparent && !req.claim_mask)
+        throw Error(PTB_E_INVALID, "first_sample != 0 on a transparent-background scene needs ptb_tile_req.claim_mask");
+    w.accum.ensure(npix * sizeof(float4));
+    w.io_a.ensure(npix * 3 * sizeof(float));
+    w.io_b.ensure(npix * sizeof(float));
+    uint8_t* mask_dev = nullptr;
+    if (transparent && req.claim_mask) {
+        w.io_c.ensure(npix);
+        mask_dev = (uint8_t*)w.io_c.p;
+    }
+    if (chained) { // the caller's running mean (and mask) continue: host → device
+        PTB_CUDA(cudaMemcpyAsync(w.io_a.p, rgb_out, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        PTB_CUDA(cudaMemcpyAsync(w.io_b.p, alpha_out, npix * sizeof(float), cudaMemcpyHostToDevice, st));
+        launch_join_rgba((const float*)w.io_a.p, (const float*)w.io_b.p, npix, (float4*)w.accum.p, st);
+        if (mask_dev) PTB_CUDA(cudaMemcpyAsync(mask_dev, req.claim_mask, npix, cudaMemcpyHostToDevice, st));
+    }
+    render_tile_locked(w, s, req, TileTarget{(float4*)w.accum.p, req.w, mask_dev}, st, stats);
     launch_split_rgba((const float4*)w.accum.p, npix, (float*)w.io_a.p, alpha_out ? (float*)w.io_b.p : nullptr, st);
     PTB_CUDA(cudaMemcpyAsync(rgb_out, w.io_a.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (alpha_out) PTB_CUDA(cudaMemcpyAsync(alpha_out, w.io_b.p, npix * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (mask_dev) PTB_CUDA(cudaMemcpyAsync(req.claim_mask, mask_dev, npix, cudaMemcpyDeviceToHost, st));
     PTB_CUDA(cudaStreamSynchronize(st));
 }
 

@@ -22,6 +22,9 @@ struct Options {
     int64_t extend_contexts = 2;                // rays per lane of the context kernel (variant 4)
     int64_t extend_sm_ranges = 0;               // every SM starts on its own contiguous part of the ray queue
     int64_t time_stages = 0;            // CUDA-event pair around every extend / shade launch (perturbs the total)
+    int64_t group_timeout_ms = 120000;  // multi-GPU: longest wait at a barrier / rendezvous before PTB_E_NCCL
+    int64_t frame_tiles_in_flight = 6;  // multi-GPU frame: host threads (streams) per GPU
+    int64_t frame_queue_depth = 1;      // tiles queued per stream (1: claim after the previous tile finished, 2: one ahead)
 };
 extern Options g_options;
 
@@ -29,6 +32,11 @@ void render_tile_dev(const ptb_scene* s, const ptb_tile_req& req, float4* rgba_d
                      ptb_render_stats* stats);
 void render_tile_host(const ptb_scene* s, const ptb_tile_req& req, float* rgb_out, float* alpha_out,
                       ptb_render_stats* stats);
+// frame driver: one tile accumulated in place at `base` (pitch pixels per row, own or peer-mapped memory),
+// asynchronous on `st`; rays / paths / launches add up in the stream's workspace until they are read
+void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, float4* base, uint32_t pitch, cudaStream_t st);
+void stream_counters_reset(int device, cudaStream_t st);
+void stream_counters_read(int device, cudaStream_t st, uint64_t* rays, uint64_t* paths, uint64_t* launches);
 void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, ptb_hit* hits_out, float* attrs_out,
                      ptb_render_stats* stats);
 void trace_rays_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, ptb_hit* hits_dev, cudaStream_t st);

@@ -22,16 +22,70 @@ namespace ptb {
 
 namespace {
 
-template <typename T>
-T* upload(ptb_scene* s, const std::vector<T>& v) {
-    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 256);
-    void* p = nullptr;
-    PTB_CUDA(cudaMalloc(&p, bytes));
-    s->allocs.push_back(p);
-    s->info.device_bytes += bytes;
-    if (!v.empty()) PTB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return static_cast<T*>(p);
+// The scene's arrays live back to back (256-byte aligned) in ONE device allocation, the blob: replicating a
+// scene onto another GPU is a single device-to-device copy (or one broadcast), no rebuild and no fix-up
+// beyond re-basing the fifteen pointers of DScene.
+struct BlobPlan {
+    struct Part {
+        const void* src;
+        size_t bytes;
+    };
+    std::vector<Part> parts;
+    template <typename T>
+    void add(const std::vector<T>& v) {
+        parts.push_back(Part{v.data(), v.size() * sizeof(T)});
+    }
+};
+
+void set_scene_pointers(ptb_scene* s) {
+    char* b = static_cast<char*>(s->blob);
+    const uint64_t* o = s->offsets;
+    DScene& d = s->d;
+    d.instances = reinterpret_cast<const DInstance*>(b + o[0]);
+    d.inst_sphere = reinterpret_cast<const float4*>(b + o[1]);
+    d.surfaces = reinterpret_cast<const DSurface*>(b + o[2]);
+    d.meshes = reinterpret_cast<const DMesh*>(b + o[3]);
+    d.kd_nodes = reinterpret_cast<const uint2*>(b + o[4]);
+    d.kd_pairs = reinterpret_cast<const uint4*>(b + o[5]);
+    d.kd_refs = reinterpret_cast<const uint32_t*>(b + o[6]);
+    d.tri = reinterpret_cast<const float4*>(b + o[7]);
+    d.vtx_pos = reinterpret_cast<const float*>(b + o[8]);
+    d.vtx_nrm = reinterpret_cast<const float*>(b + o[9]);
+    d.vtx_tan = reinterpret_cast<const float*>(b + o[10]);
+    d.vtx_uv = reinterpret_cast<const float*>(b + o[11]);
+    d.materials = reinterpret_cast<const DMaterial*>(b + o[12]);
+    d.textures = reinterpret_cast<const DTexture*>(b + o[13]);
+    d.texels = reinterpret_cast<const unsigned char*>(b + o[14]);
 }
+
+void upload_blob(ptb_scene* s, const BlobPlan& plan) {
+    if (plan.parts.size() != size_t(PTB_SCENE_ARRAYS)) throw Error(PTB_E_INVALID, "internal: blob plan");
+    uint64_t total = 0;
+    for (int i = 0; i < PTB_SCENE_ARRAYS; i++) {
+        s->offsets[i] = total;
+        total += (std::max<uint64_t>(plan.parts[i].bytes, 256) + 255) & ~uint64_t(255);
+    }
+    PTB_CUDA(cudaMalloc(&s->blob, total));
+    s->blob_bytes = total;
+    s->info.device_bytes = total;
+    for (int i = 0; i < PTB_SCENE_ARRAYS; i++)
+        if (plan.parts[i].bytes)
+            PTB_CUDA(cudaMemcpy(static_cast<char*>(s->blob) + s->offsets[i], plan.parts[i].src, plan.parts[i].bytes,
+                                cudaMemcpyHostToDevice));
+    set_scene_pointers(s);
+}
+
+constexpr uint32_t SCENE_HEADER_MAGIC = 0x42545053u; // "SPTB"
+constexpr uint32_t SCENE_HEADER_VERSION = 1;
+
+struct SceneHeader {
+    uint32_t magic, version;
+    uint64_t blob_bytes;
+    uint64_t offsets[PTB_SCENE_ARRAYS];
+    DScene d; // pointer members are meaningless outside the exporting process: re-based on import
+    ptb_scene_info info;
+    uint32_t has_pass_through, pad;
+};
 
 Xform xform_from(const float* origin, const float* basis) {
     Xform t;
@@ -147,7 +201,7 @@ void destroy_scene(ptb_scene* s) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
-    for (void* p : s->allocs) cudaFree(p);
+    if (s->blob) cudaFree(s->blob);
     cudaSetDevice(prev);
     delete s;
 }
@@ -372,21 +426,23 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
         // ---- upload ----
         auto t1 = std::chrono::steady_clock::now();
         DScene& d = s->d;
-        d.instances = upload(s, instances);
-        d.inst_sphere = upload(s, spheres);
-        d.surfaces = upload(s, surfaces);
-        d.meshes = upload(s, meshes);
-        d.kd_nodes = upload(s, nodes);
-        d.kd_pairs = upload(s, pairs);
-        d.kd_refs = upload(s, refs);
-        d.tri = upload(s, tri);
-        d.vtx_pos = upload(s, vpos);
-        d.vtx_nrm = upload(s, vnrm);
-        d.vtx_tan = upload(s, vtan);
-        d.vtx_uv = upload(s, vuv);
-        d.materials = upload(s, materials);
-        d.textures = upload(s, textures);
-        d.texels = upload(s, texels);
+        BlobPlan plan; // order = DScene's pointer members = set_scene_pointers
+        plan.add(instances);
+        plan.add(spheres);
+        plan.add(surfaces);
+        plan.add(meshes);
+        plan.add(nodes);
+        plan.add(pairs);
+        plan.add(refs);
+        plan.add(tri);
+        plan.add(vpos);
+        plan.add(vnrm);
+        plan.add(vtan);
+        plan.add(vuv);
+        plan.add(materials);
+        plan.add(textures);
+        plan.add(texels);
+        upload_blob(s, plan);
         d.n_instances = desc.n_instances;
         d.n_pairs = static_cast<uint32_t>(pairs.size());
         d.n_refs = static_cast<uint32_t>(refs.size());
@@ -420,6 +476,75 @@ ptb_scene* create_scene(const ptb_scene_desc& desc, int device) {
         throw;
     }
     return s;
+}
+
+// ---- replication ------------------------------------------------------------------------------------------------
+
+uint64_t scene_header_bytes() { return sizeof(SceneHeader); }
+
+void export_scene_header(const ptb_scene* s, void* out) {
+    SceneHeader h{};
+    h.magic = SCENE_HEADER_MAGIC;
+    h.version = SCENE_HEADER_VERSION;
+    h.blob_bytes = s->blob_bytes;
+    for (int i = 0; i < PTB_SCENE_ARRAYS; i++) h.offsets[i] = s->offsets[i];
+    h.d = s->d;
+    h.info = s->info;
+    h.has_pass_through = s->has_pass_through ? 1 : 0;
+    std::memcpy(out, &h, sizeof(h));
+}
+
+ptb_scene* import_scene(const void* header, uint64_t n_bytes, int device, const void* src_blob_dev, int src_device) {
+    require(header && n_bytes == sizeof(SceneHeader), "scene header: wrong size");
+    SceneHeader h;
+    std::memcpy(&h, header, sizeof(h));
+    require(h.magic == SCENE_HEADER_MAGIC && h.version == SCENE_HEADER_VERSION, "scene header: bad magic / version");
+    uint64_t prev_end = 0;
+    for (int i = 0; i < PTB_SCENE_ARRAYS; i++) {
+        require(h.offsets[i] >= prev_end && h.offsets[i] % 256 == 0 && h.offsets[i] < h.blob_bytes, "scene header: bad offsets");
+        prev_end = h.offsets[i];
+    }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        throw Error(PTB_E_CUDA, "no CUDA device is usable; libptb has no CPU fallback");
+    require(device >= 0 && device < n_dev, "device ordinal out of range");
+    PTB_CUDA(cudaSetDevice(device));
+    ptb_scene* s = new ptb_scene;
+    try {
+        auto t0 = std::chrono::steady_clock::now();
+        s->device = device;
+        s->replica = true;
+        cudaDeviceProp prop{};
+        PTB_CUDA(cudaGetDeviceProperties(&prop, device));
+        s->sm_count = prop.multiProcessorCount;
+        s->d = h.d;
+        s->info = h.info;
+        s->has_pass_through = h.has_pass_through != 0;
+        s->blob_bytes = h.blob_bytes;
+        for (int i = 0; i < PTB_SCENE_ARRAYS; i++) s->offsets[i] = h.offsets[i];
+        PTB_CUDA(cudaMalloc(&s->blob, s->blob_bytes));
+        set_scene_pointers(s);
+        if (src_blob_dev) {
+            if (src_device == device)
+                PTB_CUDA(cudaMemcpy(s->blob, src_blob_dev, s->blob_bytes, cudaMemcpyDeviceToDevice));
+            else
+                PTB_CUDA(cudaMemcpyPeer(s->blob, device, src_blob_dev, src_device, s->blob_bytes));
+            PTB_CUDA(cudaDeviceSynchronize());
+        }
+        s->info.build_seconds = 0; // nothing was built here
+        s->info.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } catch (...) {
+        destroy_scene(s);
+        throw;
+    }
+    return s;
+}
+
+ptb_scene* clone_scene(const ptb_scene* s, int device) {
+    require(s != nullptr, "scene is NULL");
+    SceneHeader h;
+    export_scene_header(s, &h);
+    return import_scene(&h, sizeof(h), device, s->blob, s->device);
 }
 
 } // namespace ptb

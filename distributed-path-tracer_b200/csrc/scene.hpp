@@ -10,10 +10,15 @@
 #include "kd_build.hpp"
 #include "ptb.h"
 
+constexpr int PTB_SCENE_ARRAYS = 15; // arrays inside the blob, in the order of DScene's pointer members
+
 struct ptb_scene {
     int device = 0;
-    ptb::DScene d{};            // device pointers + small by-value globals
-    std::vector<void*> allocs;  // every cudaMalloc of this scene
+    ptb::DScene d{};            // device pointers (into the blob) + small by-value globals
+    void* blob = nullptr;       // the ONE device allocation that holds every array of the scene
+    uint64_t blob_bytes = 0;
+    uint64_t offsets[PTB_SCENE_ARRAYS] = {}; // byte offset of each array inside the blob (256-byte aligned)
+    bool replica = false;       // imported / cloned: no host trees
     std::vector<ptb::KdTree> trees; // host copies, kept for ptb_scene_dump_kd
     ptb_scene_info info{};
     int sm_count = 148;
@@ -63,5 +68,10 @@ void read_png(const std::string& path, OwnedTexture& out);
 // scene.cu
 ptb_scene* create_scene(const ptb_scene_desc& desc, int device); // throws
 void destroy_scene(ptb_scene* s);
+// replication: header (plain data) + blob (one device allocation)
+uint64_t scene_header_bytes();
+void export_scene_header(const ptb_scene* s, void* out);
+ptb_scene* import_scene(const void* header, uint64_t n_bytes, int device, const void* src_blob_dev, int src_device);
+ptb_scene* clone_scene(const ptb_scene* s, int device);
 
 } // namespace ptb

@@ -28,13 +28,14 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 2
+#define PTB_ABI_VERSION 3
 
 typedef enum ptb_status {
     PTB_OK = 0,
     PTB_E_INVALID = 1, /* bad argument / malformed scene description        */
     PTB_E_CUDA = 2,    /* CUDA runtime error, or no usable device            */
-    PTB_E_NCCL = 3,    /* reserved for the multi-GPU context                 */
+    PTB_E_NCCL = 3,    /* multi-GPU exchange failed: peer access, CUDA IPC,
+                          shared-memory rendezvous or a group time-out       */
     PTB_E_OOM = 4,     /* host or device allocation failed                   */
     PTB_E_IO = 5       /* file missing / unreadable / malformed glTF         */
 } ptb_status;
@@ -228,6 +229,13 @@ typedef struct ptb_tile_req {
     uint32_t integrator;     /* ptb_integrator                                */
     uint32_t first_sample_unjittered; /* APP/processors/worker/worker.cpp:125-129 */
     uint32_t reserved;
+    /* Transparent-background scenes only (renderer.cpp:374-393 keeps a per-pixel "claimed" flag next to the
+     * running mean): w*h bytes, caller-owned, in the memory space of the output (host for ptb_render_tile,
+     * device for ptb_render_tile_dev).  Written by every call; read when first_sample != 0.  May be NULL for a
+     * call that renders all its samples at once (first_sample == 0 and no later call continues it).  Together
+     * with the output buffer — which is IN/OUT when first_sample != 0 — this is the whole state that chains
+     * sample ranges: the library keeps none of it. */
+    void* claim_mask;
 } ptb_tile_req;
 
 typedef struct ptb_render_stats {
@@ -246,12 +254,14 @@ typedef struct ptb_render_stats {
 /* Replaces renderer::render (LIB/core/renderer.cpp:334-428) /
  * worker::run's pipeline (APP/processors/worker/worker.cpp:25-105) for one
  * tile: linear running-mean radiance, row-major w*h*3, and the alpha channel
- * (w*h, may be NULL). Synchronous. */
+ * (w*h, may be NULL when first_sample == 0). Synchronous; safe to call from several
+ * host threads.  With first_sample != 0 the buffers are IN/OUT: they must hold the
+ * running mean of samples [0, first_sample) as an earlier call returned it. */
 ptb_status ptb_render_tile(const ptb_scene* scene, const ptb_tile_req* req, float* rgb_out,
                            float* alpha_out, ptb_render_stats* stats_out);
 
 /* Same, leaving the result in device memory: `rgba_dev` is a device pointer
- * to w*h float4 (rgb = mean radiance, a = alpha).  `stream` is a cudaStream_t
+ * to w*h float4 (rgb = mean radiance, a = alpha; IN/OUT when first_sample != 0).  `stream` is a cudaStream_t
  * (NULL = the default stream).  Asynchronous with respect to the host except
  * for the per-bounce queue-size read-back. */
 ptb_status ptb_render_tile_dev(const ptb_scene* scene, const ptb_tile_req* req, void* rgba_dev,
@@ -282,6 +292,98 @@ ptb_status ptb_write_png(const char* path, const uint8_t* rgba8, uint32_t w, uin
 ptb_status ptb_worker_run(const char* worker_info_json, const char* scene_dir, int device,
                           const char* png_path, uint8_t* rgba8_out, uint32_t* width_out,
                           uint32_t* height_out, ptb_render_stats* stats_out);
+
+/* ------------------------------------------------------------ multi-GPU -- */
+/*
+ * Image tiles shard across GPUs, the scene is replicated.  What the reference does with a
+ * thread pool over scanlines and a barrier per sample (LIB/core/renderer.cpp:354-407), and its worker with
+ * stage threads (APP/processors/worker/worker.cpp:25-105), is here:
+ *   - one RANK per GPU: a host thread of one process (ptb_ctx) or one process per GPU (ptb_group);
+ *   - tiles claimed from ONE shared counter (work stealing: std::atomic fetch-add, in the process heap or in a
+ *     POSIX shared-memory segment), several tiles in flight per GPU on separate streams;
+ *   - NO collective in the data path: the frame lives on rank 0's GPU and every rank's accumulate kernel
+ *     stores its finished pixels straight into it over NVLink (peer access in one process, CUDA IPC across
+ *     processes) — the tile return is fused into the kernel that produces the pixels;
+ *   - the scene is built ONCE and its flattened HBM image copied GPU → GPU (ptb_scene_clone), or broadcast
+ *     by the caller between ptb_scene_export_header / ptb_scene_import (e.g. ncclBroadcast into ptb_scene_blob).
+ * A frame rendered on N GPUs is bit-identical to the same frame on one (tiles compose exactly).
+ */
+
+/* The flattened scene is ONE device allocation ("blob") plus a small plain-data header describing it. */
+ptb_status ptb_scene_blob(const ptb_scene* scene, void** blob_dev, uint64_t* blob_bytes);
+/* Call with header == NULL to obtain the required size. */
+ptb_status ptb_scene_export_header(const ptb_scene* scene, void* header, uint64_t capacity, uint64_t* n_bytes);
+/* A replica on `device` from a header.  src_blob_dev != NULL: the blob is copied from that device pointer
+ * (cudaMemcpyPeer from src_device).  src_blob_dev == NULL: the blob is left for the caller to fill (obtain it
+ * with ptb_scene_blob, e.g. as the destination of an ncclBroadcast) before the scene is used.  Replicas hold
+ * no host copy of the trees (ptb_scene_dump_kd fails on them). */
+ptb_status ptb_scene_import(const void* header, uint64_t n_bytes, int device, const void* src_blob_dev, int src_device,
+                            ptb_scene** out);
+/* = export + import with a device-to-device copy: no rebuild, no host round trip. */
+ptb_status ptb_scene_clone(const ptb_scene* scene, int device, ptb_scene** out);
+
+#define PTB_OUT_NONE 0u    /* the frame stays in HBM on rank 0 (throughput measurements) */
+#define PTB_OUT_RGBA32F 1u /* full_w*full_h*4 floats: linear running-mean rgb + alpha     */
+#define PTB_OUT_RGBA8 2u   /* full_w*full_h*4 bytes: tonemap_approx_aces + sRGB, what worker::generate_final_image
+                              hands to the PNG encoder (APP/processors/worker/worker.cpp:172-191) */
+
+/* The worker's request over the whole frame ({samples, bounces, X, Y}, APP/models/work_info.hpp:27-30) plus how
+ * to cut it. */
+typedef struct ptb_frame_req {
+    uint32_t full_w, full_h;
+    uint32_t spp, max_depth;
+    uint64_t seed;
+    uint32_t integrator;              /* ptb_integrator */
+    uint32_t first_sample_unjittered;
+    uint32_t tile_w, tile_h;          /* the unit of work stealing; 0 = chosen by the library        */
+    uint32_t tiles_in_flight;         /* streams (host threads) per GPU; 0 = default (6)            */
+    uint32_t output;                  /* PTB_OUT_*                                                  */
+} ptb_frame_req;
+
+typedef struct ptb_frame_stats {
+    uint64_t paths, rays, kernel_launches; /* summed over all ranks                                 */
+    uint32_t n_tiles, n_ranks;
+    double gpu_seconds;   /* CUDA-event time on the slowest rank, first tile start to last tile end  */
+    double wall_seconds;  /* host clock around the whole call on rank 0, output copy included        */
+    uint64_t tiles_per_rank[16];
+    double gpu_seconds_per_rank[16];
+} ptb_frame_stats;
+
+/* One process per GPU (torchrun, MPI, ...): collective over `world` processes of ONE node that pass the same
+ * `name` (a POSIX shared-memory object "/ptb_<name>": tile counters, barrier, IPC handle of the frame).
+ * Rank 0 owns the frame.  Every call below is COLLECTIVE: all ranks call it with the same arguments.
+ * A rank that fails or does not arrive within the time-out (option "group_timeout_ms") makes every rank
+ * return PTB_E_NCCL instead of hanging. */
+typedef struct ptb_group ptb_group;
+ptb_status ptb_group_create(const char* name, int rank, int world, int device, ptb_group** out);
+void ptb_group_destroy(ptb_group* group);
+ptb_status ptb_group_barrier(ptb_group* group);
+/* `scene` is this rank's replica.  out_host (rank 0 only; others pass NULL) receives the frame in the format
+ * req->output names; pinned memory is written directly, pageable memory through a pinned staging buffer.
+ * stats_out may be NULL; it is filled on rank 0. */
+ptb_status ptb_group_render_frame(ptb_group* group, const ptb_scene* scene, const ptb_frame_req* req,
+                                  void* out_host, ptb_frame_stats* stats_out);
+
+/* One process, n_gpus GPUs, one host thread per GPU: what replaces worker::run for a multi-GPU box.
+ * devices == NULL means 0 .. n_gpus-1. */
+typedef struct ptb_ctx ptb_ctx;
+ptb_status ptb_ctx_create(int n_gpus, const int* devices, ptb_ctx** out);
+void ptb_ctx_destroy(ptb_ctx* ctx);
+/* Builds the scene once (host KD build + upload to the first device) and replicates its blob GPU → GPU. */
+ptb_status ptb_ctx_set_scene(ptb_ctx* ctx, const ptb_scene_desc* desc);
+ptb_status ptb_ctx_load_gltf(ptb_ctx* ctx, const char* path, uint32_t camera_index, uint32_t sun_light_index);
+/* The replica on the i-th GPU of the context (owned by the context). */
+const ptb_scene* ptb_ctx_scene(const ptb_ctx* ctx, int i);
+ptb_status ptb_render_frame(ptb_ctx* ctx, const ptb_frame_req* req, void* out_host, ptb_frame_stats* stats_out);
+
+/* ptb_worker_run (the Lambda worker's request → RGBA8 / PNG) with the frame tile-sharded over ctx's GPUs. */
+ptb_status ptb_worker_run_ctx(ptb_ctx* ctx, const char* worker_info_json, const char* scene_dir,
+                              const char* png_path, uint8_t* rgba8_out, uint32_t* width_out,
+                              uint32_t* height_out, ptb_frame_stats* stats_out);
+
+/* Pinned host memory for frame outputs (a plain cudaHostAlloc): lets ptb_render_frame copy without staging. */
+ptb_status ptb_host_alloc(uint64_t bytes, void** out);
+void ptb_host_free(void* p);
 
 /* ------------------------------------------------- host-only / test hooks -- */
 
@@ -342,6 +444,13 @@ ptb_status ptb_shard_publish_dev(const ptb_scene* shard, uint64_t n, const uint6
                                  void* const* peer_payload, int world, void* stream);
 ptb_status ptb_shard_unpack_dev(const uint64_t* best_keys_dev, const void* payload_dev, uint64_t n, ptb_hit* hits_dev,
                                 void* stream);
+
+/* Host-only exercise of ptb_group's rendezvous, work-stealing counter and barrier (no CUDA): `frames` rounds in
+ * which the `world` processes that pass the same `name` claim n_tiles tiles each (work_us microseconds of fake work
+ * per tile); mine_out[e * n_tiles + i] = 1 where THIS rank claimed tile i of round e.  Over all ranks every tile of
+ * every round is claimed exactly once.  A rank that never arrives → PTB_E_NCCL after "group_timeout_ms". */
+ptb_status ptb_group_selftest_host(const char* name, int rank, int world, uint32_t n_tiles, uint32_t frames,
+                                   uint32_t work_us, uint8_t* mine_out);
 
 /* Registers per thread of the extend kernel as loaded (cudaFuncGetAttributes). */
 int ptb_extend_registers(void);

@@ -29,7 +29,10 @@ def test_graft_entry_build_runs():
 
 
 def test_struct_layouts_match_header(ptb):
-    assert ctypes.sizeof(ptb.TileReq) == 56
+    assert ctypes.sizeof(ptb.TileReq) == 64  # 14 x u32 with the u64 seed at offset 32, + the claim-mask pointer
+    assert ptb.TileReq.seed.offset == 32 and ptb.TileReq.claim_mask.offset == 56
+    assert ctypes.sizeof(ptb.FrameReq) == 48 and ptb.FrameReq.seed.offset == 16
+    assert ctypes.sizeof(ptb.FrameStats) == 3 * 8 + 2 * 4 + 2 * 8 + 16 * 8 + 16 * 8
     assert ptb.HIT_DTYPE.itemsize == 28
     assert ctypes.sizeof(ptb.MaterialDesc) == 4 * (3 + 1 + 1 + 1 + 3 + 1 + 1 + 6)
     assert ctypes.sizeof(ptb.InstanceDesc) == 4 * (3 + 9 + 2)
@@ -235,3 +238,51 @@ def test_worker_request_errors_need_no_gpu(ptb, tmp_path):
     with pytest.raises(ptb.PtbError) as e:
         ptb.worker_run({"samples": 1, "bounces": 999, "X": 8, "Y": 8}, str(tmp_path))
     assert e.value.status == ptb.PTB_E_INVALID
+
+
+# ---- the multi-GPU group's host logic: rendezvous, work-stealing counter, barrier (two processes, no GPU) ----
+
+def _group_rank(name, rank, world, n_tiles, frames, q):
+    import importlib
+    ptb = importlib.import_module("distributed-path-tracer_b200")
+    try:
+        q.put((rank, ptb.group_selftest_host(name, rank, world, n_tiles, frames, work_us=200)))
+    except Exception as e:  # pragma: no cover - surfaced by the parent
+        q.put((rank, e))
+
+
+def test_group_tile_counter_and_barrier_two_processes(ptb):
+    """Two processes rendezvous through shared memory and steal tiles from one counter: over both ranks every
+    tile of every frame is claimed exactly once, both ranks get work, frames do not bleed into each other."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    name = f"test_{os.getpid()}"
+    procs = [ctx.Process(target=_group_rank, args=(name, r, 2, 64, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(2):
+        assert isinstance(got[r], np.ndarray), got[r]
+    total = got[0].astype(int) + got[1].astype(int)
+    assert total.shape == (5, 64) and np.all(total == 1)
+    assert got[0].sum() > 0 and got[1].sum() > 0
+    assert not os.path.exists("/dev/shm/ptb_" + name)  # rank 0 unlinked the name after the rendezvous
+
+
+def test_group_times_out_instead_of_hanging(ptb):
+    """A rank that never arrives: the others get PTB_E_NCCL after the time-out, nobody hangs."""
+    ptb.set_option("group_timeout_ms", 300)
+    try:
+        name = f"lonely_{os.getpid()}"
+        with pytest.raises(ptb.PtbError) as e:
+            ptb.group_selftest_host(name, 0, 2, 8, 1)
+        assert e.value.status == ptb.PTB_E_NCCL and "timed out" in str(e.value)
+    finally:
+        ptb.set_option("group_timeout_ms", 120000)
+        try:
+            os.unlink("/dev/shm/ptb_" + name)
+        except OSError:
+            pass
