@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py — the hot path's headline benchmark.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ptb|reference] [--config c2|c1|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ptb|reference] [--config c2|c1|c3|c5]
+                    [--scaling strong|weak]
 
 Metric (BASELINE.json): Mrays/s (primary + bounce + shadow rays, counted by the extend/shadow kernels)
-on the named configuration; 1080p@64spp frames/s is reported inside `config`.
+on the named configuration, and 1080p@64spp frames/s (`config.frames_per_s_1080p64`, measured).
 
-A "step" is one pass of the hot path over one frame of synthetic input:
-  * N = 1: configs[1] of BASELINE.json — the synthetic 999 698-triangle procedural heightfield,
-    1920x1080, 64 spp, depth 4 (reference library default), integrator = renderer::trace semantics;
-  * N > 1 (torchrun, one rank per GPU): the same frame at 64*N spp, cut into 32*N tiles that the ranks
-    claim from a shared counter (work stealing); per-GPU work is therefore fixed → "scaling": "weak".
-    The render has no collective; the framebuffer gather (reduce of disjoint tiles onto rank 0 over
-    NCCL) belongs to the end-to-end figure only.
-`value` is timed with CUDA events on the launching stream with the scene resident in HBM, barrier +
-synchronize on both sides, max over ranks.  `e2e` goes through the public host call
-(cluster.render_frame → libptb C ABI) and includes the request upload, the framebuffer gather and the
-device→host copy of the finished frame into pinned memory.
+A "step" is one pass of the hot path over one frame of synthetic input: configs[1] of BASELINE.json — the
+synthetic 999 698-triangle procedural heightfield, 1920x1080, 64 spp, depth 4 (reference library default),
+integrator = renderer::trace semantics.
+  * N = 1: that frame on one GPU;
+  * N > 1 (torchrun, one rank per GPU): THE SAME frame cut into tiles that the N ranks steal from one
+    shared-memory counter → "scaling": "strong" (fixed total work; what "1080p@64spp frames/s at 1/2/4/8"
+    asks).  The scene is built once on rank 0 and its flattened blob broadcast over NCCL.  There is no
+    collective in the data path: every rank's accumulate kernel stores its pixels into rank 0's frame over
+    NVLink, so the frame return is INSIDE the timed region of `value`.  The weak-scaling figure (64 spp per
+    GPU) and BASELINE's C4 (3840x2160, 1024 spp) ride along as extra objects `weak` and `c4`;
+    `--scaling weak` swaps the roles.
+`value` is timed with CUDA events on the library's streams (first tile start to last tile end, slowest rank)
+with the scene resident in HBM, barrier + synchronize on both sides.  `e2e` is host wall-clock around the
+public call (ptb_group_render_frame): request in, finished float frame copied into pinned host memory.
 
 `--impl reference` times the reference's own CPU renderer (oracle/_ref, the unmodified library compiled
 from /root/reference by oracle/Makefile; the plain-C port oracle/pt_oracle.c if that is absent) on the
@@ -198,12 +202,9 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------ product arm ----
 
-def run_ptb(args):
+def _dist_setup():
     import torch
     import torch.distributed as dist
-    import ptb200 as ptb
-    from ptb200 import cluster
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,8 +216,239 @@ def run_ptb(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         torch.cuda.set_device(0)
-    dev = torch.device("cuda", torch.cuda.current_device())
-    device_index = torch.cuda.current_device()
+    return world, rank, torch.cuda.current_device()
+
+
+def run_ptb(args):
+    """Product arm.  The frame goes through libptb's frame driver (ptb_group: one process per GPU, tiles stolen from
+    a shared-memory counter, every GPU's accumulate kernel storing into rank 0's frame over NVLink).  If that path
+    cannot be set up on this box (no peer access / CUDA IPC), all ranks fall back together to the first scheduler
+    (cluster.render_frame + NCCL reduce) and say so in `config`."""
+    import torch
+    import torch.distributed as dist
+    import ptb200 as ptb
+    from ptb200 import cluster
+
+    world, rank, device_index = _dist_setup()
+    dev = torch.device("cuda", device_index)
+    if args.gather == "nccl":
+        return run_ptb_legacy(args, world, rank, device_index, why="--gather nccl")
+
+    desc_name, full_w, full_h, spp0, depth, integ = CONFIGS[args.config]
+    if args.spp:
+        spp0 = args.spp
+    ptb.set_option("wave_paths", args.wave_paths)
+    ptb.set_option("group_timeout_ms", 180000)
+    ptb.set_option("frame_queue_depth", args.queue_depth)
+
+    # ---- the scene: built ONCE on rank 0, its flattened HBM image broadcast over NCCL
+    t0 = time.perf_counter()
+    scene = ptb.Scene.create(build_description(args.config, args.n_grid), device_index) if rank == 0 else None
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    scene = cluster.replicate_scene(scene, device_index)
+    t_replicate = time.perf_counter() - t0
+    info = scene.info()
+
+    ok = 1
+    group = None
+    try:
+        group = cluster.make_group(device_index)
+        group.render_frame(scene, 64, 32, 1, 1, output=ptb.OUT_NONE)  # maps the frame on every rank (peer / IPC)
+    except ptb.PtbError as e:
+        sys.stderr.write(f"bench.py rank {rank}: frame driver unavailable ({e}); falling back\n")
+        ok = 0
+    if world > 1:
+        t = torch.tensor([ok], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = int(t.item())
+    if not ok:
+        if group is not None:
+            group.close()
+        scene.close()
+        return run_ptb_legacy(args, world, rank, device_index, why="peer access / CUDA IPC unavailable")
+
+    pinned = torch.empty((full_h, full_w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
+    tile = tuple(args.tile)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def frame(seed, spp, to_host, w=full_w, h=full_h):
+        return group.render_frame(scene, w, h, spp, depth, out=(pinned.data_ptr() if (to_host and rank == 0) else None),
+                                  seed=seed, integrator=integ, tile=tile, tiles_in_flight=args.streams,
+                                  output=ptb.OUT_RGBA32F if to_host else ptb.OUT_NONE)
+
+    def timed(spp, steps, warmup, to_host=False, w=full_w, h=full_h):
+        """→ dict(value, ms_per_step, rays, paths, launches, ...) on rank 0 (None elsewhere): device-timed when the
+        frame stays in HBM, host-timed through the public call when it is copied out (to_host)."""
+        for i in range(warmup):
+            frame(1000 + i, spp, to_host, w, h)
+        ms_total = wall_total = 0.0
+        rays = paths = launches = 0
+        per_rank_tiles = None
+        for i in range(steps):
+            flush.fill_(i & 0xFF)  # L2 flush between timed iterations
+            barrier()
+            t0 = time.perf_counter()
+            _, st = frame(1 + i, spp, to_host, w, h)
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            barrier()
+            wall_total += cluster.all_max([wall], dev)[0]
+            if rank == 0:
+                ms_total += st["gpu_seconds"] * 1e3  # CUDA events on the library's streams, slowest rank
+                rays += st["rays"]
+                paths += st["paths"]
+                launches += st["kernel_launches"]
+                per_rank_tiles = st["tiles_per_rank"]
+        if rank != 0:
+            return None
+        t_ms = wall_total if to_host else ms_total
+        return dict(value=rays / (t_ms * 1e-3) / 1e6, ms_per_step=t_ms / steps, wall_ms_per_step=wall_total / steps,
+                    rays=rays, paths=paths, launches=launches, n_tiles=st["n_tiles"], tiles_per_rank=per_rank_tiles)
+
+    weak = args.scaling == "weak"
+    spp_main = spp0 * world if weak else spp0
+
+    # ---- timed region: kernel throughput, the finished frame stays in HBM on rank 0 (the tile return is inside)
+    sampler = ClockSampler(device_index)
+    for i in range(args.warmup):
+        frame(1000 + i, spp_main, True)
+    if rank == 0:
+        sampler.start()
+    main = timed(spp_main, args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end to end: request in, finished float frame in pinned host memory on rank 0
+    e2e = timed(spp_main, args.steps, 0, to_host=True)
+
+    # ---- the other scaling mode and the multi-GPU configurations BASELINE.json names, as extra legs
+    extra = {}
+    if world > 1 and not args.no_extra_legs:
+        other_spp = spp0 if weak else spp0 * world
+        r = timed(other_spp, max(2, min(args.steps, 5)), 1)
+        if rank == 0:
+            extra["strong" if weak else "weak"] = {
+                "value": r["value"], "unit": "Mrays/s", "ms_per_step": r["ms_per_step"], "spp_total": other_spp,
+                "what": (f"the fixed {spp0}-spp frame over {world} GPUs" if weak
+                         else f"{other_spp} spp in total ({spp0} per GPU): per-GPU work fixed")}
+        if args.config == "c2":
+            # C4: 3840x2160, 1024 spp, tile-sharded with work stealing; the frame return is part of the kernels
+            c4_w, c4_h, c4_spp = 3840, 2160, args.c4_spp
+            timed(4, 1, 0, w=c4_w, h=c4_h)  # sizes the buffers
+            r = timed(c4_spp, 1, 0, w=c4_w, h=c4_h)
+            if rank == 0:
+                extra["c4"] = {"workload": f"C4 {c4_w}x{c4_h} {c4_spp}spp depth{depth} over {world} GPUs",
+                               "value": r["value"], "unit": "Mrays/s", "s_per_frame": r["ms_per_step"] * 1e-3,
+                               "wall_s_per_frame": r["wall_ms_per_step"] * 1e-3, "n_tiles": r["n_tiles"],
+                               "tiles_per_rank": r["tiles_per_rank"], "paths": r["paths"]}
+
+    # ---- roofline of the dominant kernel (extend): separate, untimed-for-`value` passes on rank 0
+    hbm_peak, peak_src = load_peaks()
+    roofline = None
+    n_tiles_main = main["n_tiles"] if rank == 0 else 0
+    if rank == 0:
+        tiles = ptb.frame_tiles(full_w, full_h, spp_main, world, tile)
+        sample_tiles = tiles[:: max(1, world)]
+        buf = torch.zeros(max(t[2] * t[3] for t in tiles) * 4, dtype=torch.float32, device=dev)
+
+        def one_tile(t):
+            return scene.render_tile_dev(buf.data_ptr(), full_w, full_h, spp_main, depth, tile=t, seed=1, integrator=integ,
+                                         stream=torch.cuda.current_stream().cuda_stream, want_stats=True)
+        ptb.set_option("time_stages", 1)
+        st_t = [one_tile(t) for t in sample_tiles]
+        ptb.set_option("time_stages", 0)
+        ptb.set_option("count_visits", 1)
+        st_c = [one_tile(t) for t in sample_tiles]
+        ptb.set_option("count_visits", 0)
+        ext_s = sum(s["extend_seconds"] for s in st_t)
+        shade_s = sum(s["shade_seconds"] for s in st_t)
+        ext_launches = sum(s["extend_launches"] for s in st_t)
+        n_rays = sum(s["rays"] for s in st_c)
+        nb, nl, nt = (sum(s[k] for s in st_c) for k in ("node_visits", "leaf_visits", "tri_tests"))
+        alg_bytes = 32 * n_rays + 8 * nb + 8 * nl + (4 + 48) * nt + 32 * n_rays  # SURVEY.md §8(d)
+        achieved = alg_bytes / ext_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "extend_lanes_kernel", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_ray": alg_bytes / max(n_rays, 1), "rays_per_launch": n_rays / max(ext_launches, 1),
+                    "avg_launch_ms": ext_s / max(ext_launches, 1) * 1e3,
+                    "extend_share_of_step": ext_s / max(ext_s + shade_s, 1e-12),
+                    "visits_per_ray": {"branch": nb / max(n_rays, 1), "leaf": nl / max(n_rays, 1),
+                                       "tri": nt / max(n_rays, 1)},
+                    "extend_Mrays_per_s": n_rays / ext_s / 1e6,
+                    "how": "CUDA events around every extend launch of the frame's tiles rendered one at a time on rank 0"}
+        prof = os.path.join(ROOT, "profiles", "extend_traffic.json")
+        if os.path.exists(prof):
+            try:
+                # measured DRAM bytes per ray of the ncu capture x the rays one launch processes here
+                tj = json.load(open(prof))
+                roofline["traffic"] = tj["dram_bytes_per_ray"] * roofline["rays_per_launch"]
+                roofline["traffic_source"] = ("profiles/extend_traffic.json (" + str(tj.get("source", "ncu --set full")) +
+                                              "): dram bytes/ray x rays_per_launch")
+                roofline["issue"] = {"slots_busy_pct": tj.get("issue_slots_busy_pct_per_launch"),
+                                     "active_lanes_per_instruction": tj.get("active_lanes_per_instruction_per_launch"),
+                                     "long_scoreboard_cycles_per_instruction":
+                                         tj.get("stall_cycles_per_instruction_long_scoreboard_per_launch"),
+                                     "source": tj.get("summary", "profiles/")}
+            except Exception:
+                pass
+
+    # ---- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        c = cpu_reference(args.config, args.n_grid, depth, integ, sample_seconds=args.cpu_seconds)
+        cpu = {"value": c["value"], "unit": "Mrays/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
+
+    if rank == 0:
+        frames_per_s = 1e3 / main["ms_per_step"] * (world if weak else 1)
+        tw, th = ptb.frame_tiles(full_w, full_h, spp_main, world, tile)[0][2:]
+        line = {
+            "metric": "Mrays/s", "value": main["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc_name + (f", {spp_main} spp total ({spp0}/GPU)" if (weak and world > 1) else ""),
+                       "triangles": int(info["n_triangles"]), "kd_nodes": int(info["n_kd_nodes"]),
+                       "kd_leaf_refs": int(info["n_leaf_refs"]), "scene_bytes": int(info["device_bytes"]),
+                       "kd_build_s": t_build, "scene_replicate_s": t_replicate if world > 1 else None,
+                       "scene_replication": "built once on rank 0; flattened blob broadcast over NCCL" if world > 1 else None,
+                       "tiles": f"{n_tiles_main} tiles of {tw}x{th}, stolen from one shared counter, {args.streams} in flight per GPU",
+                       "tiles_per_rank": main["tiles_per_rank"],
+                       "frame_return": "accumulate kernels store into rank 0's frame over NVLink (CUDA IPC), inside the timed region",
+                       "parallelism": f"tiles x{world}", "wave_paths": args.wave_paths,
+                       "frames_per_s_1080p64": (frames_per_s if args.config in ("c2", "c5") else None),
+                       "frames_per_s_measured": not weak or world == 1,
+                       "wall_ms_per_step": main["wall_ms_per_step"],
+                       "rays_per_path": main["rays"] / max(main["paths"], 1),
+                       "l2": "256 MiB buffer written between timed iterations; scene + path state exceed L2"},
+            "e2e": {"value": e2e["value"], "unit": "Mrays/s", "h2d_bytes_per_step": int(ctypes.sizeof(ptb.FrameReq)),
+                    "d2h_bytes_per_step": int(full_w * full_h * 16), "ms_per_step": e2e["ms_per_step"],
+                    "frames_per_s": 1e3 / e2e["ms_per_step"],
+                    "what": "ptb_group_render_frame: request in, float RGBA frame in pinned host memory on rank 0"},
+            "gpu_launches": int(main["launches"]),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    group.barrier()
+    group.close()
+    scene.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_ptb_legacy(args, world, rank, device_index, why):
+    """The first scheduler (round 1): tile claims through the torch.distributed store, one NCCL reduce as the gather.
+    Weak scaling only.  Selected with --gather nccl, or automatically when the frame driver cannot map rank 0's frame."""
+    import torch
+    import torch.distributed as dist
+    import ptb200 as ptb
+    from ptb200 import cluster
+    dev = torch.device("cuda", device_index)
 
     desc_name, full_w, full_h, spp0, depth, integ = CONFIGS[args.config]
     if args.spp:
@@ -313,76 +545,24 @@ def run_ptb(args):
         barrier()
         e2e_ms += cluster.all_max([(time.perf_counter() - t0) * 1e3], dev)[0]
     e2e_value = rays_all / (e2e_ms * 1e-3) / 1e6
-    n_tiles_rank = len(tiles) / world
     h2d = int(ctypes.sizeof(ptb.TileReq) * len(tiles))
     d2h = int(full_w * full_h * 16)
-
-    # ---- roofline of the dominant kernel (extend): separate, untimed-for-`value` passes on rank 0's share
-    hbm_peak, peak_src = load_peaks()
-    roofline = None
     if rank == 0:
-        ptb.set_option("time_stages", 1)
-        st_t = [render_tile(t, frame, 1, 0, stats=True) for t in tiles[:: world]]
-        ptb.set_option("time_stages", 0)
-        ptb.set_option("count_visits", 1)
-        st_c = [render_tile(t, frame, 1, 0, stats=True) for t in tiles[:: world]]
-        ptb.set_option("count_visits", 0)
-        ext_s = sum(s["extend_seconds"] for s in st_t)
-        shade_s = sum(s["shade_seconds"] for s in st_t)
-        ext_launches = sum(s["extend_launches"] for s in st_t)
-        n_rays = sum(s["rays"] for s in st_c)
-        nb, nl, nt = (sum(s[k] for s in st_c) for k in ("node_visits", "leaf_visits", "tri_tests"))
-        alg_bytes = 32 * n_rays + 8 * nb + 8 * nl + (4 + 48) * nt + 32 * n_rays
-        achieved = alg_bytes / ext_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "extend_lanes_kernel", "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "bytes_per_ray": alg_bytes / max(n_rays, 1), "rays_per_launch": n_rays / max(ext_launches, 1),
-                    "avg_launch_ms": ext_s / max(ext_launches, 1) * 1e3,
-                    "extend_share_of_step": ext_s / max(ext_s + shade_s, 1e-12),
-                    "visits_per_ray": {"branch": nb / max(n_rays, 1), "leaf": nl / max(n_rays, 1),
-                                       "tri": nt / max(n_rays, 1)},
-                    "extend_Mrays_per_s": n_rays / ext_s / 1e6}
-        prof = os.path.join(ROOT, "profiles", "extend_traffic.json")
-        if os.path.exists(prof):
-            try:
-                # measured DRAM bytes per ray of the ncu capture x the rays one launch processes here
-                tj = json.load(open(prof))
-                roofline["traffic"] = tj["dram_bytes_per_ray"] * roofline["rays_per_launch"]
-                roofline["traffic_source"] = "profiles/extend_traffic.json: dram bytes/ray under ncu x rays_per_launch"
-                # what actually bounds the kernel (SURVEY 8d asks for the issue-rate view next to the HBM one):
-                # from the same ncu capture, per extend launch of a wave (primary, bounce 1..3)
-                roofline["issue"] = {"slots_busy_pct": tj.get("issue_slots_busy_pct_per_launch"),
-                                     "active_lanes_per_instruction": tj.get("active_lanes_per_instruction_per_launch"),
-                                     "long_scoreboard_cycles_per_instruction":
-                                         tj.get("stall_cycles_per_instruction_long_scoreboard_per_launch"),
-                                     "source": "profiles/r01_v7_extend_ncu_summary.txt"}
-            except Exception:
-                pass
-
-    # ---- CPU baseline (rank 0, N = 1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        c = cpu_reference(args.config, args.n_grid, depth, integ, sample_seconds=args.cpu_seconds)
-        cpu = {"value": c["value"], "unit": "Mrays/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
-
-    if rank == 0:
-        frames_per_s = world * 1e3 / ms_per_step  # 64-spp-equivalent frames
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc_name + (f", {spp} spp total ({spp0}/GPU)" if world > 1 else ""),
-                       "triangles": int(info["n_triangles"]), "kd_nodes": int(info["n_kd_nodes"]),
-                       "kd_leaf_refs": int(info["n_leaf_refs"]), "scene_bytes": int(info["device_bytes"]),
-                       "kd_build_s": info["build_seconds"], "tiles": f"{cols}x{rows} work-stolen, {n_workers} in flight per GPU",
+                       "fallback": f"first scheduler (torch.distributed store + NCCL reduce): {why}",
+                       "triangles": int(info["n_triangles"]), "kd_build_s": info["build_seconds"],
+                       "tiles": f"{cols}x{rows} work-stolen, {n_workers} in flight per GPU",
                        "parallelism": f"tiles x{world}", "wave_paths": args.wave_paths,
-                       "frames_per_s_1080p64": frames_per_s if args.config == "c2" else None,
                        "rays_per_path": rays_all / max(paths_all, 1),
                        "l2": "256 MiB buffer written between timed iterations; scene + path state exceed L2"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_total(tiles, spp, depth, args.wave_paths, args.steps)),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": None, "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -409,6 +589,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ptb", choices=["ptb", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the SAME frame (64 spp) over N GPUs — BASELINE's frames/s; weak: 64 spp per GPU")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="peer: libptb's frame driver (tile stores into rank 0's frame over NVLink); nccl: round-1 scheduler")
+    ap.add_argument("--tile", type=int, nargs=2, default=[0, 0], metavar=("W", "H"), help="tile size (0 0: library's choice)")
+    ap.add_argument("--queue-depth", type=int, default=1, help="tiles queued per stream (1 or 2)")
+    ap.add_argument("--c4-spp", type=int, default=1024, help="samples of the C4 leg (3840x2160) at N > 1")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the weak-scaling / C4 legs at N > 1")
     ap.add_argument("--n-grid", type=int, default=707, help="heightfield grid (707 → 999 698 triangles)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
     ap.add_argument("--tiles-per-gpu", type=int, default=32,

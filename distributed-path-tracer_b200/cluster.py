@@ -1,5 +1,12 @@
 """Tile-sharded rendering across GPUs: one process per GPU, ``torch.distributed`` for the plumbing.
 
+The product path is in libptb (``csrc/frame.cu``: ``ptb_group`` / ``ptb_ctx``): tiles stolen from a shared-memory
+counter, every GPU's accumulate kernel storing into rank 0's frame over NVLink.  This module adds the two things
+that need a process group — :func:`replicate_scene` (rank 0 builds, the flattened scene blob is broadcast over
+NCCL) and :func:`make_group` (agreeing on the rendezvous name) — and keeps the first, renderer-agnostic
+scheduler (:func:`render_frame`: tile claims through the ``torch.distributed`` store, ``reduce(SUM)`` as the
+gather), which the CPU tests drive on gloo and ``bench.py --gather nccl`` can still select.
+
 The reference distributes by GEOMETRY (every worker holds a subset of the primitives and every ray is
 meant to visit all workers, ``src/processors/worker/intersection_worker.cpp:78-110``; the transport was
 never written).  With 180 GB of HBM the scene is simply replicated and the IMAGE is sharded instead:
@@ -388,3 +395,58 @@ class ShardMergeContext:
         _check(L.ptb_shard_unpack_dev(C.c_void_p(self.keys.data_ptr()), C.c_void_p(self.payload.data_ptr()), n,
                                       C.c_void_p(hits_dev.data_ptr()), C.c_void_p(st)))
         return hits_dev
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Process-group glue for the frame driver of libptb (ptb_group): scene replication and the rendezvous name.
+
+class _DeviceBytes:
+    """A raw device allocation as something ``torch.as_tensor`` understands (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def device_bytes_tensor(ptr: int, nbytes: int, device):
+    """uint8 CUDA tensor aliasing [ptr, ptr + nbytes) — no copy; the memory stays owned by libptb."""
+    import torch
+    return torch.as_tensor(_DeviceBytes(ptr, nbytes), device=device)
+
+
+def replicate_scene(scene, device_index: int, src: int = 0, chunk_bytes: int = 256 << 20):
+    """Rank ``src`` passes its built :class:`Scene`, the others pass None.  → every rank's replica.
+
+    The scene is built ONCE: the header (a few hundred bytes of plain data) travels with ``broadcast_object_list``,
+    the flattened HBM blob with ``broadcast`` over NCCL straight from rank src's blob into the other ranks'
+    (``ptb_scene_export_header`` / ``ptb_scene_import`` / ``ptb_scene_blob``); nobody rebuilds a tree."""
+    dist = _dist()
+    if not dist or dist.get_world_size() == 1:
+        return scene
+    import torch
+    from . import Scene
+    rank = dist.get_rank()
+    dev = torch.device("cuda", device_index)
+    box = [scene.export_header() if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    if rank != src:
+        scene = Scene.import_header(box[0], device_index)  # allocates the blob, leaves it to be filled
+    ptr, nbytes = scene.blob()
+    blob = device_bytes_tensor(ptr, nbytes, dev)
+    for off in range(0, nbytes, chunk_bytes):
+        dist.broadcast(blob[off:off + chunk_bytes], src=src)
+    torch.cuda.synchronize(dev)
+    return scene
+
+
+def make_group(device_index: int):
+    """A :class:`Group` over the default process group's ranks (one node): rank 0 picks the shared-memory name."""
+    import os
+    import uuid
+    from . import Group
+    dist = _dist()
+    if not dist or dist.get_world_size() == 1:
+        return Group(f"solo_{os.getpid()}_{uuid.uuid4().hex[:8]}", 0, 1, device_index)
+    box = [f"{os.getpid()}_{uuid.uuid4().hex[:12]}" if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return Group(box[0], dist.get_rank(), dist.get_world_size(), device_index)

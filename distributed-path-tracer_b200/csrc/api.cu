@@ -446,6 +446,13 @@ ptb_status ptb_scene_clone(const ptb_scene* scene, int device, ptb_scene** out) 
     });
 }
 
+ptb_status ptb_frame_tiling(const ptb_frame_req* req, int world, uint32_t* tile_w, uint32_t* tile_h, uint32_t* n_tiles) {
+    return guarded([&] {
+        if (!req) throw ptb::Error(PTB_E_INVALID, "req is NULL");
+        ptb::frame_tiling(*req, world, tile_w, tile_h, n_tiles);
+    });
+}
+
 ptb_status ptb_group_create(const char* name, int rank, int world, int device, ptb_group** out) {
     return guarded([&] {
         if (!out) throw ptb::Error(PTB_E_INVALID, "out is NULL");

@@ -352,6 +352,14 @@ std::vector<Tile> make_tiles(const ptb_frame_req& r, int world) {
 
 } // namespace
 
+void frame_tiling(const ptb_frame_req& req, int world, uint32_t* tile_w, uint32_t* tile_h, uint32_t* n_tiles) {
+    if (req.full_w == 0 || req.full_h == 0 || world < 1) throw Error(PTB_E_INVALID, "empty frame or bad world size");
+    const std::vector<Tile> tiles = make_tiles(req, world);
+    if (tile_w) *tile_w = tiles[0].w;
+    if (tile_h) *tile_h = tiles[0].h;
+    if (n_tiles) *n_tiles = (uint32_t)tiles.size();
+}
+
 // ---- group life cycle ------------------------------------------------------------------------------------------------
 
 static void group_init_device(ptb_group* g) {

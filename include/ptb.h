@@ -349,6 +349,10 @@ typedef struct ptb_frame_stats {
     double gpu_seconds_per_rank[16];
 } ptb_frame_stats;
 
+/* The tile grid a frame request is cut into for `world` ranks (tile_w / tile_h of the request, or the library's
+ * choice when they are 0): row-major, edge tiles absorb the remainder. */
+ptb_status ptb_frame_tiling(const ptb_frame_req* req, int world, uint32_t* tile_w, uint32_t* tile_h, uint32_t* n_tiles);
+
 /* One process per GPU (torchrun, MPI, ...): collective over `world` processes of ONE node that pass the same
  * `name` (a POSIX shared-memory object "/ptb_<name>": tile counters, barrier, IPC handle of the frame).
  * Rank 0 owns the frame.  Every call below is COLLECTIVE: all ranks call it with the same arguments.
