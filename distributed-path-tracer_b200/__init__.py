@@ -153,7 +153,7 @@ EXPORTS = [
     "ptb_scene_blob", "ptb_scene_export_header", "ptb_scene_import", "ptb_scene_clone",
     "ptb_group_create", "ptb_group_destroy", "ptb_group_barrier", "ptb_group_render_frame",
     "ptb_ctx_create", "ptb_ctx_destroy", "ptb_ctx_set_scene", "ptb_ctx_load_gltf", "ptb_ctx_scene", "ptb_render_frame",
-    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host", "ptb_frame_tiling",
+    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host", "ptb_frame_tiling", "ptb_shadow_registers", "ptb_trace_occlusion",
 ]
 
 _lib = None
@@ -194,6 +194,8 @@ def lib():
     L.ptb_shard_publish_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
     L.ptb_shard_unpack_dev.restype = st
     L.ptb_shard_unpack_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.ptb_trace_occlusion.restype = st
+    L.ptb_trace_occlusion.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_void_p, C.POINTER(RenderStats)]
     L.ptb_trace_rays_stats.restype = st
     L.ptb_trace_rays_stats.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_void_p, C.POINTER(RenderStats)]
     L.ptb_camera_rays.restype = st
@@ -225,6 +227,7 @@ def lib():
     L.ptb_abi_version.restype = C.c_int
     L.ptb_device_count.restype = C.c_int
     L.ptb_extend_registers.restype = C.c_int
+    L.ptb_shadow_registers.restype = C.c_int
     L.ptb_selftest_division.restype = C.c_uint64
     L.ptb_selftest_division.argtypes = [C.c_uint64, C.c_uint64]
     L.ptb_scene_blob.restype = st
@@ -551,6 +554,14 @@ class Scene:
             return hits, at
         _check(lib().ptb_trace_rays(self.h, _fp(od), len(od), hits.ctypes.data))
         return hits
+
+    def trace_occlusion(self, origin_dir, stats=False):
+        """Shadow query (any-hit): → bool[n], True where the ray hits anything (+ stats dict with stats=True)."""
+        od = np.ascontiguousarray(origin_dir, np.float32).reshape(-1, 6)
+        occ = np.zeros(len(od), np.uint8)
+        s = RenderStats()
+        _check(lib().ptb_trace_occlusion(self.h, _fp(od), len(od), occ.ctypes.data, C.byref(s)))
+        return (occ.astype(bool), s.as_dict()) if stats else occ.astype(bool)
 
     def trace_rays_dev(self, rays_dev_ptr: int, n: int, hits_dev_ptr: int, stream: int = 0):
         """Rays (n*6 float32) and hits (n ptb_hit records, HIT_DTYPE) stay in device memory; asynchronous."""

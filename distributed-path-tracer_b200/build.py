@@ -23,12 +23,18 @@ INCLUDE = os.path.join(ROOT, "include")
 OUT = os.path.join(HERE, "libptb.so")
 OBJ = os.path.join(HERE, "build")
 
-CU_SOURCES = ["kernels.cu", "extend.cu", "extend_coop.cu", "extend_ctx.cu", "scene.cu", "render.cu", "frame.cu", "api.cu"]
+CU_SOURCES = ["kernels.cu", "extend.cu", "scene.cu", "render.cu", "frame.cu", "api.cu"]
+# losing kernel variants kept for A/B measurements (option extend_variant = 0 / 3 / 4): PTB_BUILD_EXPERIMENTS=1
+EXPERIMENTS = os.environ.get("PTB_BUILD_EXPERIMENTS", "0") not in ("", "0")
+if EXPERIMENTS:
+    CU_SOURCES += ["experiments/extend_simple.cu", "experiments/extend_coop.cu", "experiments/extend_ctx.cu"]
 CXX_SOURCES = ["kd_build.cpp", "gltf.cpp", "png.cpp"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--fmad=false", "-prec-div=true", "-prec-sqrt=true",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-I" + CSRC, "-I" + INCLUDE]
+if EXPERIMENTS:
+    NVCC_FLAGS.append("-DPTB_BUILD_EXPERIMENTS=1")
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-I" + CSRC, "-I" + INCLUDE]
 
 
@@ -75,7 +81,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     nvcc, cxx = _nvcc(), _cxx()
     for src in CU_SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src + ".o")
+        o = os.path.join(OBJ, src.replace("/", "_") + ".o")
         if force or _stale(o, [s] + headers):
             extra = ["-Xptxas", "-v"] if ptxas_info else []
             _run([nvcc, "-ccbin", cxx] + ARCH + NVCC_FLAGS + extra + ["-c", s, "-o", o], verbose or ptxas_info)

@@ -165,6 +165,11 @@ ptb_status ptb_trace_rays_stats(const ptb_scene* scene, const float* origin_dir,
     return guarded([&] { ptb::trace_rays_host(scene, origin_dir, n, hits_out, nullptr, stats_out); });
 }
 
+ptb_status ptb_trace_occlusion(const ptb_scene* scene, const float* origin_dir, uint64_t n, uint8_t* occluded_out,
+                               ptb_render_stats* stats_out) {
+    return guarded([&] { ptb::trace_occlusion_host(scene, origin_dir, n, occluded_out, stats_out); });
+}
+
 ptb_status ptb_camera_rays(const ptb_scene* scene, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py,
                            const float* aa, uint64_t n, float* origin_dir_out) {
     return guarded([&] {
@@ -239,6 +244,11 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
             ptb::g_options.count_visits = value ? 1 : 0;
         } else if (n == "extend_variant") {
             if (value < 0 || value > 4 || value == 2) throw ptb::Error(PTB_E_INVALID, "extend_variant must be 0, 1, 3 or 4");
+#ifndef PTB_BUILD_EXPERIMENTS
+            if (value != 1)
+                throw ptb::Error(PTB_E_INVALID, "extend_variant " + std::to_string(value) +
+                                                    " is an experiment: rebuild with PTB_BUILD_EXPERIMENTS=1");
+#endif
             ptb::g_options.extend_variant = value;
         } else if (n == "extend_steps") {
             if (value < 2 || value > 4) throw ptb::Error(PTB_E_INVALID, "extend_steps must be 2..4");
@@ -545,10 +555,14 @@ int ptb_device_count(void) {
     return n;
 }
 int ptb_extend_registers(void) {
+#ifdef PTB_BUILD_EXPERIMENTS
     if (ptb::g_options.extend_variant == 3) return ptb::extend_coop_regs_per_thread();
     if (ptb::g_options.extend_variant == 4) return ptb::extend_ctx_regs_per_thread((int)ptb::g_options.extend_contexts);
-    return ptb::g_options.extend_variant == 0 ? ptb::extend_regs_per_thread() : ptb::extend_lanes_regs_per_thread();
+    if (ptb::g_options.extend_variant == 0) return ptb::extend_regs_per_thread();
+#endif
+    return ptb::extend_lanes_regs_per_thread();
 }
+int ptb_shadow_registers(void) { return ptb::extend_anyhit_regs_per_thread(); }
 uint64_t ptb_selftest_division(uint64_t n, uint64_t seed) { return ptb::division_selftest(n, seed); }
 
 } // extern "C"

@@ -3,10 +3,15 @@
 //   raygen      one thread per (pixel, sample) of the wave   LIB/core/renderer.cpp:359-370, APP worker.cpp:117-146
 //   extend      persistent warps pulling 32-ray batches from an atomic head;
 //               closest hit per ray (trace_device.cuh)        LIB/core/renderer.cpp:645-675
+//   shadow_gen  (scenes with a sun) one thread per live path: the cone-jittered
+//               shadow ray of this shade event, compacted into the shadow queue;
+//               the any-hit instantiation of the extend kernel (extend.cu)
+//               resolves the queue before shade runs            LIB/core/renderer.cpp:498-511,
+//                                                               APP intersection_worker.cpp:22-40,49-67
 //   shade       one thread per live path: attributes, material, emission,
-//               (sun: shadow ray traced in place), BSDF sampling, throughput,
-//               Russian roulette; survivors are compacted into the next
-//               queue with one atomicAdd per warp             LIB/core/renderer.cpp:437-643, APP worker.cpp:285-514
+//               direct light from the resolved shadow ray, BSDF sampling,
+//               throughput, Russian roulette; survivors are compacted into the
+//               next queue with one atomicAdd per warp        LIB/core/renderer.cpp:437-643, APP worker.cpp:285-514
 //   accumulate  one thread per pixel: the reference's sequential running
 //               mean over the wave's samples                  LIB/core/renderer.cpp:373-399
 //   tonemap     ACES approximation + sRGB encode + RGBA8      LIB/core/utils.hpp:29-36, LIB/image/image.cpp:143-154
@@ -33,22 +38,13 @@ namespace ptb {
 
 namespace {
 
-constexpr int EXT_THREADS = 128;
 constexpr int SHADE_THREADS = 128;
-constexpr size_t STACK_SMEM_BYTES = size_t(KD_STACK_DEPTH) * 3 * sizeof(uint32_t); // per thread
 
 // flags packed in ray_d.w
 constexpr uint32_t F_BOUNCE_MASK = 0xFFu;  // bounces remaining
 constexpr uint32_t F_EVENT_SHIFT = 8;      // shade events so far (RNG counter), 16 bits
 constexpr uint32_t F_EVENT_MASK = 0xFFFFu;
 constexpr uint32_t F_PRIMARY = 1u << 24;   // no opaque surface interaction yet (alpha bookkeeping of renderer::trace)
-
-__device__ __forceinline__ KdStack make_stack(uint32_t* smem) {
-    KdStack s;
-    s.base = smem + threadIdx.x;
-    s.stride = blockDim.x;
-    return s;
-}
 
 // Slots walk the tile in 8x4 pixel blocks (a warp's primary rays form a compact bundle), the blocks in
 // super-blocks of 8x8 (64x32 pixels), so that a stretch of the queue is a compact patch of the image and the
@@ -127,56 +123,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// ------------------------------------------------------------- extend ------
-
-template <bool COUNT>
-__global__ void __launch_bounds__(EXT_THREADS)
-    extend_kernel(DScene S, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                  uint4* __restrict__ hits, float* __restrict__ t_out, const uint32_t* __restrict__ n_ptr,
-                  uint32_t* __restrict__ head, DeviceCounters* __restrict__ counters) {
-    extern __shared__ uint32_t smem[];
-    const KdStack stack = make_stack(smem);
-    const uint32_t n = *n_ptr;
-    const int lane = threadIdx.x & 31;
-    TraceCounters cnt{0, 0, 0, 0};
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(head, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t k = base + lane;
-        if (k < n) {
-            const float4 o4 = ray_o[k], d4 = ray_d[k];
-            const SceneHit h = scene_closest<COUNT>(S, V3{o4.x, o4.y, o4.z}, V3{d4.x, d4.y, d4.z}, stack, cnt);
-            uint4 rec;
-            rec.x = (h.t >= 0) ? ((h.instance << HIT_SURFACE_BITS) | h.surface) : HIT_MISS;
-            rec.y = h.tri;
-            rec.z = __float_as_uint(h.beta);
-            rec.w = __float_as_uint(h.gamma);
-            hits[k] = rec;
-            if (t_out) t_out[k] = h.t;
-            cnt.rays++;
-        }
-    }
-    // one atomic per warp for the ray count (always), visit counters only when asked for
-    unsigned long long r = cnt.rays;
-    for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
-    if (lane == 0 && r) atomicAdd(&counters->rays, r);
-    if (COUNT) {
-        unsigned long long a = cnt.node_visits, b = cnt.leaf_visits, c = cnt.tri_tests;
-        for (int o = 16; o; o >>= 1) {
-            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
-            c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-        }
-        if (lane == 0) {
-            atomicAdd(&counters->node_visits, a);
-            atomicAdd(&counters->leaf_visits, b);
-            atomicAdd(&counters->tri_tests, c);
-        }
-    }
-}
-
 // -------------------------------------------------------------- shade ------
 
 struct PathState {
@@ -191,11 +137,23 @@ struct PathState {
 // math::is_approx (LIB/math/math.inl:49-52)
 __device__ __forceinline__ bool is_approx(float a, float b) { return a == b || fabsf(a - b) < kEpsilon; }
 
+// The shadow ray of a shade event and its answer.  The reference traces it in the middle of the shade function
+// (renderer.cpp:505-511; the staged worker: intersection_worker.cpp:22-40 builds it, :49-67 resolves it).  Here
+// the shade code runs twice over a path when the scene has a sun: once to GENERATE the ray (everything up to the
+// point where the reference calls intersect(), same instructions, same random numbers, then stop), and — after
+// the any-hit kernel has resolved the whole queue — once more to USE the answer.
+struct ShadowIO {
+    V3 o, d;      // GENERATE: the shadow ray (origin, normalised direction)
+    bool emit;    // GENERATE: this event casts a shadow ray
+    bool visible; // USE: nothing between the hit point and the sun
+};
+enum : int { SHADOW_NONE = 0, SHADOW_GENERATE = 1, SHADOW_USE = 2 };
+
 // Shades one path.  Returns true when the path continues (state updated in
 // place), false when it ended (result holds what the pixel sample receives).
-template <bool APP_RR, bool HAS_SUN>
+template <bool APP_RR, bool HAS_SUN, int SHADOW>
 __device__ __forceinline__ bool shade_path(const DScene& S, const WaveGeom& g, const RenderParams& rp, PathState& st,
-                                           const uint4 hit, const KdStack& stack, TraceCounters& cnt, float4& result) {
+                                           const uint4 hit, ShadowIO& shadow, float4& result) {
     const uint32_t bounce = st.flags & F_BOUNCE_MASK;
     const uint32_t event = (st.flags >> F_EVENT_SHIFT) & F_EVENT_MASK;
     const bool primary = (st.flags & F_PRIMARY) != 0;
@@ -261,12 +219,16 @@ __device__ __forceinline__ bool shade_path(const DScene& S, const WaveGeom& g, c
         direct_incoming = rand_cone_vec(u01(rb.x), cosf(u01(rb.y) * S.sun.angular_radius), S.sun.direction);
         sun_above = dot(normal, direct_incoming) > 0;
         if (sun_above) {
-            const V3 so = at.position + direct_incoming * kEpsilon;
-            const SceneHit sh = scene_closest<false>(S, so, normalize(direct_incoming), stack, cnt);
-            cnt.rays++;
-            sun_visible = !(sh.t >= 0);
+            if (SHADOW == SHADOW_GENERATE) {
+                shadow.o = at.position + direct_incoming * kEpsilon;
+                shadow.d = normalize(direct_incoming); // geometry::ray's constructor
+                shadow.emit = true;
+                return false;
+            }
+            sun_visible = shadow.visible; // !intersect(shadow ray).hit, resolved by the any-hit kernel
         }
     }
+    if (SHADOW == SHADOW_GENERATE) return false;
 
     if (APP_RR && m.shadow_catcher && bounce == rp.max_depth) { // worker.cpp:353-389
         if (!(HAS_SUN && sun_visible)) {
@@ -345,16 +307,58 @@ __device__ __forceinline__ bool shade_path(const DScene& S, const WaveGeom& g, c
     return true;
 }
 
+// Scenes with a sun: the shadow ray of every live path's shade event, compacted into the shadow queue.
+// shadow_slot[k] = the path's position in that queue (0xFFFFFFFF: this event casts none).
+template <bool APP_RR>
+__global__ void __launch_bounds__(SHADE_THREADS)
+    shadow_gen_kernel(DScene S, WaveGeom g, RenderParams rp, const float4* __restrict__ ray_o,
+                      const float4* __restrict__ ray_d, const uint4* __restrict__ hits, float4* __restrict__ sh_o,
+                      float4* __restrict__ sh_d, uint32_t* __restrict__ shadow_slot, const uint32_t* __restrict__ n_ptr,
+                      uint32_t* __restrict__ n_shadow) {
+    const uint32_t n = *n_ptr;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_warp = (n + 31u) & ~31u;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_warp; k += gridDim.x * blockDim.x) {
+        ShadowIO sh;
+        sh.emit = false;
+        sh.visible = false;
+        if (k < n) {
+            const float4 o4 = __ldg(ray_o + k), d4 = __ldg(ray_d + k);
+            PathState st;
+            st.o = V3{o4.x, o4.y, o4.z};
+            st.d = V3{d4.x, d4.y, d4.z};
+            st.thr = V3{1.0f, 1.0f, 1.0f};
+            st.rad = V3{0.0f, 0.0f, 0.0f};
+            st.alpha = 1.0f;
+            st.p = __float_as_uint(o4.w);
+            st.flags = __float_as_uint(d4.w);
+            float4 unused;
+            shade_path<APP_RR, true, SHADOW_GENERATE>(S, g, rp, st, __ldg(hits + k), sh, unused);
+        }
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, sh.emit);
+        uint32_t base = 0;
+        if (lane == 0 && mask) base = atomicAdd(n_shadow, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (k < n) {
+            uint32_t slot = 0xFFFFFFFFu;
+            if (sh.emit) {
+                slot = base + __popc(mask & ((1u << lane) - 1u));
+                __stcs(sh_o + slot, make_float4(sh.o.x, sh.o.y, sh.o.z, 0.0f));
+                __stcs(sh_d + slot, make_float4(sh.d.x, sh.d.y, sh.d.z, 0.0f));
+            }
+            shadow_slot[k] = slot;
+        }
+    }
+}
+
 template <bool APP_RR, bool HAS_SUN>
 __global__ void __launch_bounds__(SHADE_THREADS)
     shade_kernel(DScene S, WaveGeom g, RenderParams rp, PathBuffers in, const uint4* __restrict__ hits,
                  PathBuffers out, float4* __restrict__ sample_out, const uint32_t* __restrict__ n_ptr,
-                 uint32_t* __restrict__ n_next, DeviceCounters* __restrict__ counters) {
-    extern __shared__ uint32_t smem[];
-    const KdStack stack = make_stack(smem);
+                 uint32_t* __restrict__ n_next, const uint32_t* __restrict__ shadow_slot,
+                 const uint8_t* __restrict__ occluded) {
     const uint32_t n = *n_ptr;
     const int lane = threadIdx.x & 31;
-    TraceCounters cnt{0, 0, 0, 0};
     const uint32_t n_warp = (n + 31u) & ~31u;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_warp; k += gridDim.x * blockDim.x) {
         bool alive = false;
@@ -369,8 +373,15 @@ __global__ void __launch_bounds__(SHADE_THREADS)
             st.alpha = r4.w;
             st.p = __float_as_uint(o4.w);
             st.flags = __float_as_uint(d4.w);
+            ShadowIO sh;
+            sh.emit = false;
+            sh.visible = false;
+            if (HAS_SUN) {
+                const uint32_t slot = __ldcs(shadow_slot + k);
+                if (slot != 0xFFFFFFFFu) sh.visible = __ldcs(occluded + slot) == 0;
+            }
             float4 result;
-            alive = shade_path<APP_RR, HAS_SUN>(S, g, rp, st, __ldcs(hits + k), stack, cnt, result);
+            alive = shade_path<APP_RR, HAS_SUN, HAS_SUN ? SHADOW_USE : SHADOW_NONE>(S, g, rp, st, __ldcs(hits + k), sh, result);
             if (!alive) __stcs(sample_out + st.p, result);
         }
         const unsigned mask = __ballot_sync(0xFFFFFFFFu, alive);
@@ -384,11 +395,6 @@ __global__ void __launch_bounds__(SHADE_THREADS)
             __stcs(out.thr + k2, make_float4(st.thr.x, st.thr.y, st.thr.z, 0.0f));
             __stcs(out.rad + k2, make_float4(st.rad.x, st.rad.y, st.rad.z, st.alpha));
         }
-    }
-    if (HAS_SUN) {
-        unsigned long long r = cnt.rays;
-        for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
-        if (lane == 0 && r) atomicAdd(&counters->rays, r);
     }
 }
 
@@ -564,41 +570,38 @@ void launch_raygen(const DScene& S, const WaveGeom& g, const RenderParams& rp, c
     raygen_kernel<<<grid_for(n, 256, cfg.sm_count * 8), 256, 0, st>>>(S, g, rp, out, sample_out, qcount0);
 }
 
-void launch_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
-                   const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
-                   cudaStream_t st) {
-    const size_t smem = STACK_SMEM_BYTES * EXT_THREADS;
-    int per_sm = 0; // persistent grid: no more blocks than are resident at once
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel<false>, EXT_THREADS, smem) != cudaSuccess ||
-        per_sm <= 0)
-        per_sm = 4;
-    const int grid = cfg.sm_count * (per_sm < cfg.extend_blocks_per_sm ? per_sm : cfg.extend_blocks_per_sm);
-    if (cfg.count_visits)
-        extend_kernel<true><<<grid, EXT_THREADS, smem, st>>>(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters);
+void launch_shadow_gen(const DScene& S, const WaveGeom& g, const RenderParams& rp, const float4* ray_o,
+                       const float4* ray_d, const uint4* hits, float4* sh_o, float4* sh_d, uint32_t* shadow_slot,
+                       const uint32_t* n_ptr, uint32_t* n_shadow, const LaunchCfg& cfg, cudaStream_t st) {
+    const int grid = cfg.sm_count * cfg.shade_blocks_per_sm;
+    if (rp.integrator == 1)
+        shadow_gen_kernel<true><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, ray_o, ray_d, hits, sh_o, sh_d, shadow_slot, n_ptr,
+                                                                 n_shadow);
     else
-        extend_kernel<false><<<grid, EXT_THREADS, smem, st>>>(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters);
+        shadow_gen_kernel<false><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, ray_o, ray_d, hits, sh_o, sh_d, shadow_slot, n_ptr,
+                                                                  n_shadow);
 }
 
 void launch_shade(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& in,
                   const uint4* hits, const PathBuffers& out, float4* sample_out, const uint32_t* n_ptr,
-                  uint32_t* n_next, DeviceCounters* counters, const LaunchCfg& cfg, cudaStream_t st) {
+                  uint32_t* n_next, const uint32_t* shadow_slot, const uint8_t* occluded, const LaunchCfg& cfg,
+                  cudaStream_t st) {
     const int grid = cfg.sm_count * cfg.shade_blocks_per_sm;
     const bool sun = S.sun.enabled != 0;
-    const size_t smem = sun ? STACK_SMEM_BYTES * SHADE_THREADS : 0;
     if (rp.integrator == 1) {
         if (sun)
-            shade_kernel<true, true><<<grid, SHADE_THREADS, smem, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr,
-                                                                         n_next, counters);
+            shade_kernel<true, true><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr, n_next,
+                                                                      shadow_slot, occluded);
         else
-            shade_kernel<true, false><<<grid, SHADE_THREADS, smem, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr,
-                                                                          n_next, counters);
+            shade_kernel<true, false><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr, n_next,
+                                                                       nullptr, nullptr);
     } else {
         if (sun)
-            shade_kernel<false, true><<<grid, SHADE_THREADS, smem, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr,
-                                                                          n_next, counters);
+            shade_kernel<false, true><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr, n_next,
+                                                                       shadow_slot, occluded);
         else
-            shade_kernel<false, false><<<grid, SHADE_THREADS, smem, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr,
-                                                                           n_next, counters);
+            shade_kernel<false, false><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr, n_next,
+                                                                        nullptr, nullptr);
     }
 }
 
@@ -715,12 +718,6 @@ void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cu
 void launch_camera_rays(const DScene& S, uint32_t w, uint32_t h, const uint32_t* px, const uint32_t* py, const float* aa,
                         uint64_t n, float* origin_dir, cudaStream_t st) {
     camera_rays_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, st>>>(S, w, h, px, py, aa, n, origin_dir);
-}
-
-int extend_regs_per_thread() {
-    cudaFuncAttributes a{};
-    if (cudaFuncGetAttributes(&a, extend_kernel<false>) != cudaSuccess) return -1;
-    return a.numRegs;
 }
 
 } // namespace ptb

@@ -62,12 +62,15 @@ struct LaunchCfg {
 // qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.
 void launch_raygen(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& out,
                    float4* sample_out, uint32_t* qcount0, const LaunchCfg& cfg, cudaStream_t st);
-void launch_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
-                   const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
-                   cudaStream_t st);
+// scenes with a sun: shade event → shadow queue (sh_o / sh_d, compacted; shadow_slot[k] = position or 0xFFFFFFFF)
+void launch_shadow_gen(const DScene& S, const WaveGeom& g, const RenderParams& rp, const float4* ray_o,
+                       const float4* ray_d, const uint4* hits, float4* sh_o, float4* sh_d, uint32_t* shadow_slot,
+                       const uint32_t* n_ptr, uint32_t* n_shadow, const LaunchCfg& cfg, cudaStream_t st);
+// shadow_slot / occluded: what launch_shadow_gen and launch_extend_anyhit produced (null without a sun)
 void launch_shade(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& in,
                   const uint4* hits, const PathBuffers& out, float4* sample_out, const uint32_t* n_ptr,
-                  uint32_t* n_next, DeviceCounters* counters, const LaunchCfg& cfg, cudaStream_t st);
+                  uint32_t* n_next, const uint32_t* shadow_slot, const uint8_t* occluded, const LaunchCfg& cfg,
+                  cudaStream_t st);
 // dst: the tile's pixel (0,0) inside a buffer with `pitch` pixels per row (own or peer-mapped memory);
 // fresh: this wave starts the running mean (dst / claimed are not read)
 void launch_accumulate(const WaveGeom& g, const float4* sample_out, float4* dst, uint32_t pitch, uint8_t* claimed,
@@ -107,7 +110,7 @@ void launch_shard_unpack(const unsigned long long* best_keys, const uint4* paylo
                          cudaStream_t st);
 void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st);
 
-// extend.cu — the lane-state-machine closest-hit kernel (default); launch_extend is the first, simple kernel
+// extend.cu — the lane-state-machine closest-hit kernel
 void launch_extend_lanes(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
                          const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
                          cudaStream_t st);
@@ -116,7 +119,18 @@ void launch_extend_lanes(const DScene& S, const float4* ray_o, const float4* ray
 void launch_extend_lanes_merge(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
                                const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const MergeArgs* merge_dev,
                                const LaunchCfg& cfg, cudaStream_t st);
+// the SHADOW kernel: the any-hit instantiation of the same kernel; occluded[k] = 1 when ray k hits anything
+void launch_extend_anyhit(const DScene& S, const float4* ray_o, const float4* ray_d, uint8_t* occluded,
+                          const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
+                          cudaStream_t st);
 int extend_lanes_regs_per_thread();
+int extend_anyhit_regs_per_thread();
+
+// ---- experiments (csrc/experiments/, built only with PTB_BUILD_EXPERIMENTS=1; option extend_variant) ----
+// extend_simple.cu — the first kernel: one thread per ray, shared-memory stack
+void launch_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
+                   const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
+                   cudaStream_t st);
 // extend_coop.cu — lane state machine + warp-cooperative leaf tests
 void launch_extend_coop(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
                         const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,

@@ -53,6 +53,7 @@ struct DeviceBuf {
 struct Workspace {
     DeviceBuf path[2][4]; // ping-pong × {ray_o, ray_d, thr, rad}
     DeviceBuf hits, t, sample_out, counters, qcount, accum, claimed, io_a, io_b, io_c;
+    DeviceBuf sh_o, sh_d, sh_slot, sh_occluded; // shadow queue of a shade event (scenes with a sun)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> stage_ev; // pool for per-launch timing (option time_stages)
     std::mutex lock;
@@ -89,14 +90,12 @@ PathBuffers path_set(Workspace& w, int i) {
 
 void run_extend(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
                 const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg, cudaStream_t st) {
-    if (cfg.extend_variant == 0)
-        launch_extend(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
-    else if (cfg.extend_variant == 3)
-        launch_extend_coop(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
-    else if (cfg.extend_variant == 4)
-        launch_extend_ctx(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
-    else
-        launch_extend_lanes(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
+#ifdef PTB_BUILD_EXPERIMENTS
+    if (cfg.extend_variant == 0) return launch_extend(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
+    if (cfg.extend_variant == 3) return launch_extend_coop(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
+    if (cfg.extend_variant == 4) return launch_extend_ctx(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
+#endif
+    launch_extend_lanes(S, ray_o, ray_d, hits, t_out, n_ptr, head, counters, cfg, st);
 }
 
 LaunchCfg launch_cfg(const ptb_scene* s) {
@@ -158,7 +157,15 @@ void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& re
     w.sample_out.ensure(cap * sizeof(float4));
     const uint32_t n_iters_fixed = req.max_depth;
     const size_t n_counters = size_t(n_iters_fixed) + MAX_EXTRA_ITERS + 2;
-    w.qcount.ensure(n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t));
+    const bool sun = s->d.sun.enabled != 0;
+    // per iteration: queue size + extend's work heads; with a sun the same again for the shadow queue
+    w.qcount.ensure(n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t) * (sun ? 2 : 1));
+    if (sun) {
+        w.sh_o.ensure(cap * sizeof(float4));
+        w.sh_d.ensure(cap * sizeof(float4));
+        w.sh_slot.ensure(cap * sizeof(uint32_t));
+        w.sh_occluded.ensure(cap);
+    }
     if (!w.counters.p) {
         w.counters.ensure(sizeof(DeviceCounters));
         PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
@@ -176,20 +183,14 @@ void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& re
 
     uint32_t* qcount = (uint32_t*)w.qcount.p;
     uint32_t* qhead = qcount + n_counters;
+    uint32_t* qshadow = qhead + n_counters * QHEAD_STRIDE; // shadow-queue sizes and heads (sun only)
+    uint32_t* qshadow_head = qshadow + n_counters;
     DeviceCounters* counters = (DeviceCounters*)w.counters.p;
     const LaunchCfg cfg = launch_cfg(s);
-
-    // May a path need more shade events than max_depth?  Only through stochastic
-    // opacity or shadow-catcher pass-through.
-    const bool may_pass_through = s->has_pass_through;
-
-    if (stats) PTB_CUDA(cudaMemsetAsync(counters, 0, sizeof(DeviceCounters), st));
-    if (stats) PTB_CUDA(cudaEventRecord(w.ev[0], st));
-
     uint64_t launches = 0, extend_launches = 0, paths = 0;
     const bool time_stages = g_options.time_stages != 0 && stats != nullptr;
     size_t n_stage_ev = 0;            // events used: [2k], [2k+1] bracket launch k
-    std::vector<uint8_t> stage_kind;  // 0 extend, 1 shade (+raygen/accumulate)
+    std::vector<uint8_t> stage_kind;  // 0 extend / shadow, 1 shade (+raygen/accumulate)
     auto stage_begin = [&](uint8_t kind) {
         if (!time_stages) return;
         PTB_CUDA(cudaEventRecord(w.stage_event(n_stage_ev++), st));
@@ -199,6 +200,42 @@ void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& re
         if (!time_stages) return;
         PTB_CUDA(cudaEventRecord(w.stage_event(n_stage_ev++), st));
     };
+    // one iteration of the wavefront: closest hit for every live path, [sun: shadow rays generated, resolved by
+    // the any-hit kernel,] shade (terminate or emit the next ray)
+    auto iteration = [&](uint32_t it, const PathBuffers& in, const PathBuffers& out, const WaveGeom& g,
+                         const RenderParams& rp) {
+        stage_begin(0);
+        run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[size_t(it) * QHEAD_STRIDE],
+                   counters, cfg, st);
+        stage_end();
+        launches++;
+        extend_launches++;
+        if (sun) {
+            stage_begin(1);
+            launch_shadow_gen(s->d, g, rp, in.ray_o, in.ray_d, (const uint4*)w.hits.p, (float4*)w.sh_o.p, (float4*)w.sh_d.p,
+                              (uint32_t*)w.sh_slot.p, &qcount[it], &qshadow[it], cfg, st);
+            stage_end();
+            stage_begin(0);
+            launch_extend_anyhit(s->d, (const float4*)w.sh_o.p, (const float4*)w.sh_d.p, (uint8_t*)w.sh_occluded.p,
+                                 &qshadow[it], &qshadow_head[size_t(it) * QHEAD_STRIDE], counters, cfg, st);
+            stage_end();
+            launches += 2;
+            extend_launches++;
+        }
+        stage_begin(1);
+        launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it], &qcount[it + 1],
+                     (const uint32_t*)w.sh_slot.p, (const uint8_t*)w.sh_occluded.p, cfg, st);
+        stage_end();
+        launches++;
+    };
+
+    // May a path need more shade events than max_depth?  Only through stochastic
+    // opacity or shadow-catcher pass-through.
+    const bool may_pass_through = s->has_pass_through;
+
+    if (stats) PTB_CUDA(cudaMemsetAsync(counters, 0, sizeof(DeviceCounters), st));
+    if (stats) PTB_CUDA(cudaEventRecord(w.ev[0], st));
+
     if (req.spp == 0 && req.first_sample == 0) { // renderer::render with sample_count 0 leaves the cleared image
         PTB_CUDA(cudaMemset2DAsync(dst.base, size_t(dst.pitch) * sizeof(float4), 0, size_t(req.w) * sizeof(float4), req.h, st));
     }
@@ -206,7 +243,7 @@ void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& re
         g.wave_samples = (uint32_t)std::min<uint64_t>(wave_samples, req.spp - s0);
         g.first_sample = req.first_sample + s0;
         paths += uint64_t(req.w) * req.h * g.wave_samples;
-        PTB_CUDA(cudaMemsetAsync(qcount, 0, n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t), st));
+        PTB_CUDA(cudaMemsetAsync(qcount, 0, n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t) * (sun ? 2 : 1), st));
         stage_begin(1);
         launch_raygen(s->d, g, rp, path_set(w, 0), (float4*)w.sample_out.p, &qcount[0], cfg, st);
         stage_end();
@@ -214,17 +251,7 @@ void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& re
         int cur = 0;
         uint32_t it = 0;
         for (; it < n_iters_fixed; it++) {
-            const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
-            stage_begin(0);
-            run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it], &qhead[size_t(it) * QHEAD_STRIDE],
-                       counters, cfg, st);
-            stage_end();
-            stage_begin(1);
-            launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
-                         &qcount[it + 1], counters, cfg, st);
-            stage_end();
-            launches += 2;
-            extend_launches++;
+            iteration(it, path_set(w, cur), path_set(w, cur ^ 1), g, rp);
             cur ^= 1;
         }
         if (may_pass_through && n_iters_fixed > 0) {
@@ -233,17 +260,7 @@ void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& re
                 PTB_CUDA(cudaMemcpyAsync(&live, &qcount[it], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
                 PTB_CUDA(cudaStreamSynchronize(st));
                 if (live == 0) break;
-                const PathBuffers in = path_set(w, cur), out = path_set(w, cur ^ 1);
-                stage_begin(0);
-                run_extend(s->d, in.ray_o, in.ray_d, (uint4*)w.hits.p, nullptr, &qcount[it],
-                           &qhead[size_t(it) * QHEAD_STRIDE], counters, cfg, st);
-                stage_end();
-                stage_begin(1);
-                launch_shade(s->d, g, rp, in, (const uint4*)w.hits.p, out, (float4*)w.sample_out.p, &qcount[it],
-                             &qcount[it + 1], counters, cfg, st);
-                stage_end();
-                launches += 2;
-                extend_launches++;
+                iteration(it, path_set(w, cur), path_set(w, cur ^ 1), g, rp);
                 cur ^= 1;
             }
         }
@@ -432,6 +449,57 @@ void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, pt
         std::memset(stats, 0, sizeof(*stats));
         stats->rays = hc.rays;
         stats->kernel_launches = 3;
+        stats->extend_launches = 1;
+        stats->gpu_seconds = stats->extend_seconds = ms * 1e-3;
+        stats->node_visits = hc.node_visits;
+        stats->leaf_visits = hc.leaf_visits;
+        stats->tri_tests = hc.tri_tests;
+    }
+}
+
+// Shadow query for an explicit ray set: the any-hit kernel the wavefront uses for sun shadow rays.
+void trace_occlusion_host(const ptb_scene* s, const float* origin_dir, uint64_t n, uint8_t* occluded_out,
+                          ptb_render_stats* stats) {
+    if (!s) throw Error(PTB_E_INVALID, "scene is NULL");
+    if (n == 0) return;
+    if (!origin_dir || !occluded_out) throw Error(PTB_E_INVALID, "rays or occluded_out is NULL");
+    if (n >= (1ull << 31)) throw Error(PTB_E_INVALID, "too many rays in one call (max 2^31 - 1)");
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device);
+    std::lock_guard<std::mutex> guard(w.lock);
+    w.events();
+    cudaStream_t st = nullptr;
+    w.io_a.ensure(n * 6 * sizeof(float));
+    w.io_b.ensure(n);
+    w.path[0][0].ensure(n * sizeof(float4));
+    w.path[0][1].ensure(n * sizeof(float4));
+    w.qcount.ensure((1 + QHEAD_STRIDE) * sizeof(uint32_t));
+    w.counters.ensure(sizeof(DeviceCounters));
+    uint32_t* qc = (uint32_t*)w.qcount.p;
+    const uint32_t init[1] = {(uint32_t)n};
+    PTB_CUDA(cudaMemsetAsync(qc, 0, (1 + QHEAD_STRIDE) * sizeof(uint32_t), st));
+    PTB_CUDA(cudaMemcpyAsync(qc, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
+    PTB_CUDA(cudaMemcpyAsync(w.io_a.p, origin_dir, n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    launch_prep_rays((const float*)w.io_a.p, n, (float4*)w.path[0][0].p, (float4*)w.path[0][1].p, st);
+    PTB_CUDA(cudaEventRecord(w.ev[0], st));
+    launch_extend_anyhit(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint8_t*)w.io_b.p, &qc[0], &qc[1],
+                         (DeviceCounters*)w.counters.p, launch_cfg(s), st);
+    PTB_CUDA(cudaEventRecord(w.ev[1], st));
+    PTB_CUDA(cudaMemcpyAsync(occluded_out, w.io_b.p, n, cudaMemcpyDeviceToHost, st));
+    DeviceCounters hc{};
+    PTB_CUDA(cudaMemcpyAsync(&hc, w.counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    PTB_CUDA(cudaStreamSynchronize(st));
+    PTB_CUDA(cudaGetLastError());
+    if (hc.bound_errors)
+        throw Error(PTB_E_CUDA, "instrumented shadow kernel: " + std::to_string(hc.bound_errors) +
+                                    " index / stack bound violations");
+    if (stats) {
+        float ms = 0;
+        PTB_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1]));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->rays = hc.rays;
+        stats->kernel_launches = 2;
         stats->extend_launches = 1;
         stats->gpu_seconds = stats->extend_seconds = ms * 1e-3;
         stats->node_visits = hc.node_visits;

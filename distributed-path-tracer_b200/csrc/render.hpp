@@ -39,6 +39,8 @@ void stream_counters_reset(int device, cudaStream_t st);
 void stream_counters_read(int device, cudaStream_t st, uint64_t* rays, uint64_t* paths, uint64_t* launches);
 void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, ptb_hit* hits_out, float* attrs_out,
                      ptb_render_stats* stats);
+void trace_occlusion_host(const ptb_scene* s, const float* origin_dir, uint64_t n, uint8_t* occluded_out,
+                          ptb_render_stats* stats);
 void trace_rays_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, ptb_hit* hits_dev, cudaStream_t st);
 void shard_reset_dev(uint64_t* keys_dev, uint64_t n, cudaStream_t st);
 void shard_trace_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, const uint32_t* instance_map_dev,

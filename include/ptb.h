@@ -251,6 +251,15 @@ typedef struct ptb_render_stats {
                                created with counters enabled (ptb_set_option) */
 } ptb_render_stats;
 
+/* Shadow query for an explicit ray set: replaces the SECOND intersect call of a shade event,
+ * `!intersect(shadow_ray).hit` (LIB/core/renderer.cpp:505-511; the staged worker:
+ * APP/processors/worker/intersection_worker.cpp:49-67).  occluded_out[i] = 1 when ray i hits anything.  Runs the
+ * any-hit instantiation of the extend kernel, the one the wavefront resolves its sun shadow rays with: it stops at
+ * the first accepted triangle of the first leaf that holds one, and equals (ptb_trace_rays(...).instance != PTB_MISS)
+ * ray for ray.  stats_out may be NULL (rays, kernel time, visit counters with "count_visits"). */
+ptb_status ptb_trace_occlusion(const ptb_scene* scene, const float* origin_dir, uint64_t n, uint8_t* occluded_out,
+                               ptb_render_stats* stats_out);
+
 /* Replaces renderer::render (LIB/core/renderer.cpp:334-428) /
  * worker::run's pipeline (APP/processors/worker/worker.cpp:25-105) for one
  * tile: linear running-mean radiance, row-major w*h*3, and the alpha channel
@@ -456,8 +465,10 @@ ptb_status ptb_shard_unpack_dev(const uint64_t* best_keys_dev, const void* paylo
 ptb_status ptb_group_selftest_host(const char* name, int rank, int world, uint32_t n_tiles, uint32_t frames,
                                    uint32_t work_us, uint8_t* mine_out);
 
-/* Registers per thread of the extend kernel as loaded (cudaFuncGetAttributes). */
+/* Registers per thread of the extend kernel / of its any-hit (shadow) instantiation as loaded
+ * (cudaFuncGetAttributes). */
 int ptb_extend_registers(void);
+int ptb_shadow_registers(void);
 
 /* The extend kernel computes the split-plane distance (split - o) / d
  * (LIB/core/mesh.cpp:336-337) through a per-ray reciprocal and three FMAs, the
@@ -472,9 +483,10 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
  *   "wave_paths"            paths per wavefront (default 8 Mi)
  *   "count_visits"          0/1: instrumented extend kernel (node / leaf / triangle visit counters)
  *   "time_stages"           0/1: CUDA events around every extend / shade launch (extend_seconds, shade_seconds)
- *   "extend_variant"        1: lane state machine with ray replacement (default); 0: first one-thread-per-ray
- *                           kernel; 3: warp-cooperative leaf tests; 4: several ray contexts per lane,
- *                           traversal state in shared memory (2 was an L1-prefetch experiment, removed)
+ *   "extend_variant"        1: lane state machine with ray replacement (default).  Only in a library built with
+ *                           PTB_BUILD_EXPERIMENTS=1 (csrc/experiments/): 0: first one-thread-per-ray kernel;
+ *                           3: warp-cooperative leaf tests; 4: several ray contexts per lane, traversal state in
+ *                           shared memory
  *   "extend_contexts"       rays per lane of variant 4 (2..4)
  *   "extend_steps", "extend_tests"   node steps (2..4) / triangle tests (1..2) offered per loop iteration
  *   "extend_setup_lanes"    waiting lanes that trigger the set-up section (1..32, default 8)
@@ -482,6 +494,9 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
  *   "path_order"            1: a wave's samples of one 8x4 pixel block are adjacent in the queue (default);
  *                           0: sample planes
  *   "extend_blocks_per_sm", "shade_blocks_per_sm"   caps on the persistent grids
+ *   "frame_tiles_in_flight" multi-GPU frame: streams (host threads) per GPU (default 6)
+ *   "frame_queue_depth"     multi-GPU frame: tiles queued per stream (1 or 2)
+ *   "group_timeout_ms"      multi-GPU: longest wait at a barrier / rendezvous before PTB_E_NCCL (default 120 000)
  * Unknown names or out-of-range values → PTB_E_INVALID.
  * Environment: PTB_OPTIONS="name=value,name=value" applies options when the library is loaded;
  * PTB_KD_CACHE=<directory> caches flattened KD trees on disk (keyed by a hash of everything a tree depends

@@ -38,7 +38,11 @@ VARIANTS = {"simple": (0, 2), "lanes": (1, 2), "coop": (3, 2), "ctx2": (4, 2), "
 def extend_variant(ptb, request):
     """Every extend kernel the library carries (extend_variant / extend_contexts), default restored afterwards."""
     variant, contexts = VARIANTS[request.param]
-    ptb.set_option("extend_variant", variant)
+    try:
+        ptb.set_option("extend_variant", variant)
+    except ptb.PtbError as e:  # the losing variants are only in a library built with PTB_BUILD_EXPERIMENTS=1
+        assert variant != 1 and "PTB_BUILD_EXPERIMENTS" in str(e)
+        pytest.skip("experiment kernels are not in the default build")
     ptb.set_option("extend_contexts", contexts)
     yield request.param
     ptb.set_option("extend_variant", 1)
@@ -300,7 +304,10 @@ def test_device_resident_trace_and_single_rank_shard_merge(ptb, cornell):
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     out = torch.zeros_like(hits)
     for variant in (1, 3):  # fused exchange in the default kernel; separate key kernel behind any other
-        ptb.set_option("extend_variant", variant)
+        try:
+            ptb.set_option("extend_variant", variant)
+        except ptb.PtbError:
+            continue  # experiments are not in the default build
         try:
             assert L.ptb_shard_reset_dev(C.c_void_p(keys.data_ptr()), n, st) == 0
             assert L.ptb_shard_trace_dev(cornell.h, C.c_void_p(rays.data_ptr()), n, C.c_void_p(imap.data_ptr()), kp, 1, st) == 0
@@ -374,23 +381,25 @@ def test_tonemap_matches_reference_encode(ptb):
     assert np.array_equal(got[:, 3], t["rgba8"][:, 3])  # alpha has no pow: exact
 
 
-@pytest.mark.parametrize("name,mode,depth", [("A", 0, 4), ("B", 1, 8)])
+@pytest.mark.parametrize("name,mode,depth", [("A", 0, 4), ("B", 1, 8), ("B16", 1, 16)])
 def test_image_statistics_against_converged_reference(cornell, name, mode, depth):
-    """Linear radiance, Cornell 64x64.  Tolerances: per-channel image mean within 4 sigma of the
-    converged reference image (sigma from the reference's own per-pixel sample variance), RMSE against it
-    within [0.6, 1.5] x the value that variance predicts, and the rays-per-path ratio of the reference."""
+    """Linear radiance, Cornell 64x64.  Tolerances (BASELINE.json's north_star): per-channel image mean within
+    3 sigma of the 16 384-spp converged reference image (sigma from the reference's own per-pixel sample variance),
+    RMSE against it within [0.6, 1.5] x the value that variance predicts, and the rays-per-path ratio of the
+    reference.  A = config C1's integrator (renderer::trace, depth 4); B16 = config C3's (worker::trace_iter,
+    depth 16, Russian roulette)."""
     conv = H.load(f"cornell_converged_{name}.npz")
-    assert int(conv["depth"]) == depth
+    assert int(conv["depth"]) == depth and int(conv["spp"]) == 16384
     spp = 512
     rgb, alpha, st = cornell.render_tile(64, 64, spp, depth, seed=99, integrator=mode)
     assert not np.isnan(rgb).any()
     z = H.mean_z(rgb, conv, spp)
-    assert np.all(np.abs(z) < 4.0), z
+    assert np.all(np.abs(z) < 3.0), z
     rmse = np.sqrt(((rgb - conv["mean"]) ** 2).mean())
     expect = np.sqrt((conv["sigma_per_sample"].astype(np.float64) ** 2).mean() * (1.0 / spp + 1.0 / float(conv["spp"])))
     assert 0.6 * expect < rmse < 1.5 * expect, (rmse, expect)
     assert np.all(alpha == 1.0)
-    want_rpp = 3.82 if mode == 0 else 5.03
+    want_rpp = {"A": 3.82, "B": 5.03, "B16": 5.49}[name]
     assert abs(st["rays"] / st["paths"] - want_rpp) < 0.05
     # per-pixel: the deviations from the converged value are noise-sized (the APP_RR estimator is
     # heavy-tailed — throughput may reach 10 — so the bound is on the bulk and on the worst pixel)
@@ -549,3 +558,71 @@ def test_worker_request_adapter(ptb, procedural, tmp_path):
     info["scene_info"]["work"] = all_work
     rgba2, st2 = ptb.worker_run(info, str(scene_dir))
     assert rgba2.shape == (480, 640, 4) and st2["paths"] == 640 * 480 * 50
+
+
+# ---- the shadow stage: shade emits shadow rays, the any-hit kernel resolves them ---------------------------------
+
+def test_shadow_kernel_equals_closest_hit_existence(ptb, procedural, cornell):
+    """ptb_trace_occlusion (the any-hit instantiation of the extend kernel, what the wavefront resolves sun shadow
+    rays with) == `ptb_trace_rays(...).instance != MISS`, ray for ray — on the golden ray sets of every fixture scene
+    (incl. the 58 740-triangle jack-of-blades and the transformed two-instance sun scene), on a 49-instance scene, and
+    it visits FEWER nodes than the closest-hit search (it leaves at the first accepted triangle)."""
+    assert ptb.lib().ptb_shadow_registers() > 0
+    r = H.load("cornell_rays.npz")
+    for key in ("cam", "rnd", "bounce"):
+        occ = cornell.trace_occlusion(r[key + "_rays"])
+        assert np.array_equal(occ, r[key + "_hits"]["instance"] != ptb.MISS), key
+    for scene_file in ("sun_scene_rays.npz", "jack_geometry_rays.npz", "textured_scene_rays.npz"):
+        z = H.load(scene_file)
+        with ptb.Scene.create(H.make_flat(ptb.SceneDescription, H.scene_parts_from_npz(z))) as s:
+            for key in ("cam", "rnd", "bounce"):
+                occ = s.trace_occlusion(z[key + "_rays"])
+                assert np.array_equal(occ, z[key + "_hits"]["instance"] != ptb.MISS), (scene_file, key)
+    rng = np.random.default_rng(3)
+    d = procedural.instanced_heightfield_scene(60, 7)
+    with ptb.Scene.create(d) as s:
+        od = np.concatenate([rng.uniform(-30, 30, (200000, 3)) * (1, 0.1, 1) + (0, 1.5, 0), rng.normal(size=(200000, 3))], 1)
+        od = od.astype(np.float32)
+        hits = s.trace_rays(od)
+        occ = s.trace_occlusion(od)
+        assert np.array_equal(occ, hits["instance"] != ptb.MISS)
+        assert 0.2 < occ.mean() < 0.98
+        ptb.set_option("count_visits", 1)
+        try:
+            _, st_full = s.trace_rays(od, stats=True)
+            _, st_any = s.trace_occlusion(od, stats=True)
+        finally:
+            ptb.set_option("count_visits", 0)
+        assert st_any["rays"] == st_full["rays"] == len(od)
+        assert st_any["tri_tests"] < st_full["tri_tests"] and st_any["node_visits"] <= st_full["node_visits"]
+    assert cornell.trace_occlusion(np.zeros((0, 6), np.float32)).shape == (0,)
+
+
+def test_sun_scene_shadow_stage_accounting(ptb, procedural):
+    """A scene with a sun: every shade event above the horizon of the light casts one shadow ray through the shadow
+    queue (rays = closest-hit rays + shadow rays), shadows darken the image, renders are deterministic and tiles /
+    wave sizes compose bit-exactly with the staged shadow pipeline too."""
+    d = procedural.heightfield_scene(64)
+    a = np.float32(0.9)
+    basis = np.array([1, 0, 0, 0, np.cos(a), -np.sin(a), 0, np.sin(a), np.cos(a)], np.float32)  # sun high in the sky
+    d_sun = procedural.heightfield_scene(64)
+    d_sun.sun = (basis, np.array([3, 3, 3], np.float32), 0.02)
+    with ptb.Scene.create(d) as s0, ptb.Scene.create(d_sun) as s1:
+        rgb0, _, st0 = s0.render_tile(160, 90, 8, 4, seed=5)
+        rgb1, _, st1 = s1.render_tile(160, 90, 8, 4, seed=5)
+        assert st1["rays"] > st0["rays"] * 1.3           # shadow rays are counted
+        assert st1["kernel_launches"] == st0["kernel_launches"] + 2 * 4  # shadow_gen + any-hit per iteration
+        assert rgb1.mean() > rgb0.mean()                 # direct light arrives
+        again, _, st2 = s1.render_tile(160, 90, 8, 4, seed=5)
+        assert np.array_equal(H.bits(rgb1), H.bits(again)) and st2["rays"] == st1["rays"]
+        tiled = np.zeros_like(rgb1)
+        for (x0, y0, w, h) in ((0, 0, 72, 40), (72, 0, 88, 40), (0, 40, 72, 50), (72, 40, 88, 50)):
+            t, _, _ = s1.render_tile(160, 90, 8, 4, tile=(x0, y0, w, h), seed=5)
+            tiled[y0:y0 + h, x0:x0 + w] = t
+        assert np.array_equal(H.bits(rgb1), H.bits(tiled))
+        ptb.set_option("wave_paths", 160 * 90 * 3)
+        try:
+            small, _, _ = s1.render_tile(160, 90, 8, 4, seed=5)
+        finally:
+            ptb.set_option("wave_paths", 8 << 20)
+        assert np.array_equal(H.bits(rgb1), H.bits(small))
