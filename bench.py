@@ -48,6 +48,7 @@ CONFIGS = {
     "c1": ("C1 cornell-box 256x256 16spp depth4 LIB", 256, 256, 16, 4, 0),
     "c2": ("C2 heightfield 999698 tris 1920x1080 64spp depth4 LIB", 1920, 1080, 64, 4, 0),
     "c3": ("C3 cornell-box 1920x1080 256spp depth16 APP_RR", 1920, 1080, 256, 16, 1),
+    "c2sun": ("C2 heightfield 999698 tris + a sun (one shadow ray per shade event) 1920x1080 64spp depth4 LIB", 1920, 1080, 64, 4, 0),
     "c5": ("C5 49 instances x 999698-tri heightfield (49M instanced tris) 1920x1080 64spp depth4 LIB", 1920, 1080, 64, 4, 0),
 }
 
@@ -118,6 +119,12 @@ def build_description(cfg_name, n_grid):
     from ptb200 import procedural as P
     if cfg_name == "c2":
         return P.heightfield_scene(n_grid)
+    if cfg_name == "c2sun":
+        d = P.heightfield_scene(n_grid)
+        a = np.float32(0.9)  # the light's -z axis tilted 0.9 rad off the vertical: long shadows over the terrain
+        basis = np.array([1, 0, 0, 0, np.cos(a), -np.sin(a), 0, np.sin(a), np.cos(a)], np.float32)
+        d.sun = (basis, np.array([3, 3, 3], np.float32), 0.004732)  # sun_light.hpp:9-10 angular radius
+        return d
     if cfg_name == "c5":
         return P.instanced_heightfield_scene(n_grid, 7)
     return ptb.load_gltf_description(P.cornell_gltf_path())
