@@ -488,7 +488,8 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
  *                           3: warp-cooperative leaf tests; 4: several ray contexts per lane, traversal state in
  *                           shared memory
  *   "extend_contexts"       rays per lane of variant 4 (2..4)
- *   "extend_steps", "extend_tests"   node steps (2..4) / triangle tests (1..2) offered per loop iteration
+ *   "extend_steps", "extend_tests"   tree levels (2 / 4 / 6: one, two or three double steps) / triangle tests (1..2)
+ *                           offered per loop iteration
  *   "extend_setup_lanes"    waiting lanes that trigger the set-up section (1..32, default 8)
  *   "extend_sm_ranges"      0/1: every SM starts on its own contiguous range of the ray queue (default 0)
  *   "path_order"            1: a wave's samples of one 8x4 pixel block are adjacent in the queue (default);
