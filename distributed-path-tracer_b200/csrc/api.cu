@@ -274,6 +274,8 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "frame_tiles_in_flight") {
             if (value < 1 || value > 16) throw ptb::Error(PTB_E_INVALID, "frame_tiles_in_flight must be 1..16");
             ptb::g_options.frame_tiles_in_flight = value;
+        } else if (n == "frame_spin_wait") {
+            ptb::g_options.frame_spin_wait = value ? 1 : 0;
         } else if (n == "frame_queue_depth") {
             if (value < 1 || value > 2) throw ptb::Error(PTB_E_INVALID, "frame_queue_depth must be 1 or 2");
             ptb::g_options.frame_queue_depth = value;

@@ -112,6 +112,7 @@ struct ptb_group {
         std::thread th;
         cudaStream_t st = nullptr;
         cudaEvent_t done[2] = {nullptr, nullptr}; // blocking-sync events, ring of tiles in flight on this stream
+        cudaEvent_t done_spin[2] = {nullptr, nullptr}; // the same, waited for by spinning (option frame_spin_wait)
         cudaEvent_t fin = nullptr;
         uint64_t rays = 0, paths = 0, launches = 0, tiles = 0;
     };
@@ -129,6 +130,7 @@ struct ptb_group {
     std::atomic<uint32_t>* job_counter = nullptr;
     float4* job_frame = nullptr;
     int job_depth = 1;
+    bool job_spin = false;
     std::string job_error;
     ptb_status job_status = PTB_OK;
 };
@@ -193,9 +195,10 @@ void worker_main(ptb_group* g, ptb_group::Worker* w, int index) {
             bool outstanding[2] = {false, false};
             int slot = 0;
             w->tiles = 0;
+            cudaEvent_t* done = g->job_spin ? w->done_spin : w->done;
             for (;;) {
                 if (outstanding[slot]) { // keep at most job_depth tiles queued on this stream
-                    PTB_CUDA(cudaEventSynchronize(w->done[slot]));
+                    PTB_CUDA(cudaEventSynchronize(done[slot]));
                     outstanding[slot] = false;
                 }
                 if (g->sh->failed.load(std::memory_order_acquire)) throw Error(PTB_E_NCCL, "group: another rank failed");
@@ -217,7 +220,7 @@ void worker_main(ptb_group* g, ptb_group::Worker* w, int index) {
                 tr.first_sample_unjittered = fr.first_sample_unjittered;
                 // straight into the frame on rank 0's GPU: base = the tile's first pixel, pitch = the frame's width
                 render_tile_into(g->job_scene, tr, g->job_frame + size_t(t.y0) * fr.full_w + t.x0, fr.full_w, w->st);
-                PTB_CUDA(cudaEventRecord(w->done[slot], w->st));
+                PTB_CUDA(cudaEventRecord(done[slot], w->st));
                 outstanding[slot] = true;
                 slot = (slot + 1) % g->job_depth;
                 w->tiles++;
@@ -251,6 +254,7 @@ void ensure_workers(ptb_group* g, int n) {
         auto* w = new ptb_group::Worker;
         PTB_CUDA(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
         for (auto& e : w->done) PTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventBlockingSync | cudaEventDisableTiming));
+        for (auto& e : w->done_spin) PTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         PTB_CUDA(cudaEventCreateWithFlags(&w->fin, cudaEventDisableTiming));
         const int index = (int)g->workers.size();
         g->workers.push_back(w);
@@ -468,6 +472,8 @@ void group_destroy(ptb_group* g) {
         if (w->st) cudaStreamDestroy(w->st);
         for (auto& e : w->done)
             if (e) cudaEventDestroy(e);
+        for (auto& e : w->done_spin)
+            if (e) cudaEventDestroy(e);
         if (w->fin) cudaEventDestroy(w->fin);
         delete w;
     }
@@ -549,6 +555,7 @@ void group_render_frame(ptb_group* g, const ptb_scene* scene, const ptb_frame_re
         g->job_counter = &sh->counter[e & 1u];
         g->job_frame = frame;
         g->job_depth = g_options.frame_queue_depth >= 2 ? 2 : 1;
+        g->job_spin = g_options.frame_spin_wait != 0;
         g->job_status = PTB_OK;
         g->job_error.clear();
         g->job_workers = n_workers;

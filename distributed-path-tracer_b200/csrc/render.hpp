@@ -24,6 +24,7 @@ struct Options {
     int64_t time_stages = 0;            // CUDA-event pair around every extend / shade launch (perturbs the total)
     int64_t group_timeout_ms = 120000;  // multi-GPU: longest wait at a barrier / rendezvous before PTB_E_NCCL
     int64_t frame_tiles_in_flight = 6;  // multi-GPU frame: host threads (streams) per GPU
+    int64_t frame_spin_wait = 0;        // workers wait for their tiles by spinning instead of sleeping on a blocking event
     int64_t frame_queue_depth = 1;      // tiles queued per stream (1: claim after the previous tile finished, 2: one ahead)
 };
 extern Options g_options;

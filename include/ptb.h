@@ -497,6 +497,7 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
  *   "extend_blocks_per_sm", "shade_blocks_per_sm"   caps on the persistent grids
  *   "frame_tiles_in_flight" multi-GPU frame: streams (host threads) per GPU (default 6)
  *   "frame_queue_depth"     multi-GPU frame: tiles queued per stream (1 or 2)
+ *   "frame_spin_wait"       multi-GPU frame: 1 = workers spin on their tile's event instead of sleeping (default 0)
  *   "group_timeout_ms"      multi-GPU: longest wait at a barrier / rendezvous before PTB_E_NCCL (default 120 000)
  * Unknown names or out-of-range values → PTB_E_INVALID.
  * Environment: PTB_OPTIONS="name=value,name=value" applies options when the library is loaded;
