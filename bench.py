@@ -358,7 +358,9 @@ def run_ptb(args):
     roofline = None
     n_tiles_main = main["n_tiles"] if rank == 0 else 0
     if rank == 0:
-        tiles = ptb.frame_tiles(full_w, full_h, spp_main, world, tile)
+        # the kernel's roofline is a property of the kernel on this workload, not of how many GPUs share the frame:
+        # always the one-GPU tiling (large waves), every world-th tile when the frame is shared
+        tiles = ptb.frame_tiles(full_w, full_h, spp_main, 1, tile)
         sample_tiles = tiles[:: max(1, world)]
         buf = torch.zeros(max(t[2] * t[3] for t in tiles) * 4, dtype=torch.float32, device=dev)
 
@@ -411,7 +413,9 @@ def run_ptb(args):
 
     if rank == 0:
         frames_per_s = 1e3 / main["ms_per_step"] * (world if weak else 1)
-        tw, th = ptb.frame_tiles(full_w, full_h, spp_main, world, tile)[0][2:]
+        tl = ptb.frame_tiles(full_w, full_h, spp_main, world, tile)
+        tile_desc = f"{tl[0][2]}x{tl[0][3]}" + (f" first, {tl[-len(tl) // 3][2]}x{tl[-len(tl) // 3][3]} last (guided)"
+                                                if tl[0][2:] != tl[-len(tl) // 3][2:] else "")
         line = {
             "metric": "Mrays/s", "value": main["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
@@ -421,7 +425,8 @@ def run_ptb(args):
                        "kd_leaf_refs": int(info["n_leaf_refs"]), "scene_bytes": int(info["device_bytes"]),
                        "kd_build_s": t_build, "scene_replicate_s": t_replicate if world > 1 else None,
                        "scene_replication": "built once on rank 0; flattened blob broadcast over NCCL" if world > 1 else None,
-                       "tiles": f"{n_tiles_main} tiles of {tw}x{th}, stolen from one shared counter, {args.streams} in flight per GPU",
+                       "tiles": f"{n_tiles_main} tiles of {tile_desc}, stolen from one shared counter, "
+                                f"{args.streams or 8} in flight per GPU",
                        "tiles_per_rank": main["tiles_per_rank"],
                        "frame_return": "accumulate kernels store into rank 0's frame over NVLink (CUDA IPC), inside the timed region",
                        "parallelism": f"tiles x{world}", "wave_paths": args.wave_paths,
@@ -474,7 +479,7 @@ def run_ptb_legacy(args, world, rank, device_index, why):
     cols, rows = cluster.tile_grid_for(world, tiles_per_gpu)
     tiles = cluster.make_tiles(full_w, full_h, cols, rows)
     frame = torch.zeros((full_h, full_w, 4), dtype=torch.float32, device=dev)
-    n_workers = max(1, args.streams)
+    n_workers = max(1, args.streams or 6)
     main_stream = torch.cuda.current_stream()
     streams = [main_stream] + [torch.cuda.Stream(device=dev) for _ in range(n_workers - 1)]
     max_px = max(t[2] * t[3] for t in tiles)
@@ -609,7 +614,7 @@ def main():
     ap.add_argument("--tiles-per-gpu", type=int, default=32,
                     help="tiles per GPU (work-stolen); more tiles = a shorter tail when ranks finish unevenly")
     ap.add_argument("--wave-paths", type=int, default=8 << 20)
-    ap.add_argument("--streams", type=int, default=6, help="tiles in flight per GPU (host threads / CUDA streams)")
+    ap.add_argument("--streams", type=int, default=0, help="tiles in flight per GPU (host threads / CUDA streams); 0 = library default (8)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of one reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

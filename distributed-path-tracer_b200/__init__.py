@@ -153,7 +153,7 @@ EXPORTS = [
     "ptb_scene_blob", "ptb_scene_export_header", "ptb_scene_import", "ptb_scene_clone",
     "ptb_group_create", "ptb_group_destroy", "ptb_group_barrier", "ptb_group_render_frame",
     "ptb_ctx_create", "ptb_ctx_destroy", "ptb_ctx_set_scene", "ptb_ctx_load_gltf", "ptb_ctx_scene", "ptb_render_frame",
-    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host", "ptb_frame_tiling", "ptb_shadow_registers", "ptb_trace_occlusion",
+    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host", "ptb_frame_tiles", "ptb_shadow_registers", "ptb_trace_occlusion",
 ]
 
 _lib = None
@@ -265,8 +265,8 @@ def lib():
     L.ptb_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
     L.ptb_host_free.restype = None
     L.ptb_host_free.argtypes = [C.c_void_p]
-    L.ptb_frame_tiling.restype = st
-    L.ptb_frame_tiling.argtypes = [C.POINTER(FrameReq), C.c_int, u32p, u32p, u32p]
+    L.ptb_frame_tiles.restype = st
+    L.ptb_frame_tiles.argtypes = [C.POINTER(FrameReq), C.c_int, u32p, C.c_uint64, u32p]
     L.ptb_group_selftest_host.restype = st
     L.ptb_group_selftest_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     _lib = L
@@ -626,14 +626,13 @@ def _frame_req(full_w, full_h, spp, max_depth, seed=1, integrator=INTEGRATOR_LIB
 
 
 def frame_tiles(full_w, full_h, spp, world=1, tile=(0, 0)):
-    """The tile grid ptb_render_frame cuts a frame into → list of (x0, y0, w, h), row-major."""
+    """The tiles ptb_render_frame cuts a frame into for `world` ranks → list of (x0, y0, w, h) in claim order."""
     req = _frame_req(full_w, full_h, spp, 1, tile=tile)
-    tw, th, n = C.c_uint32(), C.c_uint32(), C.c_uint32()
-    _check(lib().ptb_frame_tiling(C.byref(req), world, C.byref(tw), C.byref(th), C.byref(n)))
-    tiles = [(x, y, min(tw.value, full_w - x), min(th.value, full_h - y))
-             for y in range(0, full_h, th.value) for x in range(0, full_w, tw.value)]
-    assert len(tiles) == n.value
-    return tiles
+    n = C.c_uint32()
+    _check(lib().ptb_frame_tiles(C.byref(req), world, None, 0, C.byref(n)))
+    xywh = np.zeros((n.value, 4), np.uint32)
+    _check(lib().ptb_frame_tiles(C.byref(req), world, _up(xywh), n.value, C.byref(n)))
+    return [tuple(int(v) for v in t) for t in xywh]
 
 
 def _frame_out(req: FrameReq, out):

@@ -261,6 +261,9 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "extend_contexts") {
             if (value < 2 || value > 4) throw ptb::Error(PTB_E_INVALID, "extend_contexts must be 2..4");
             ptb::g_options.extend_contexts = value;
+        } else if (n == "extend_rays_per_lane") {
+            if (value < 0 || value > 4096) throw ptb::Error(PTB_E_INVALID, "extend_rays_per_lane must be 0..4096");
+            ptb::g_options.extend_rays_per_lane = value;
         } else if (n == "extend_sm_ranges") {
             ptb::g_options.extend_sm_ranges = value != 0;
         } else if (n == "extend_tests") {
@@ -274,6 +277,8 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "frame_tiles_in_flight") {
             if (value < 1 || value > 16) throw ptb::Error(PTB_E_INVALID, "frame_tiles_in_flight must be 1..16");
             ptb::g_options.frame_tiles_in_flight = value;
+        } else if (n == "frame_guided_tiles") {
+            ptb::g_options.frame_guided_tiles = value ? 1 : 0;
         } else if (n == "frame_spin_wait") {
             ptb::g_options.frame_spin_wait = value ? 1 : 0;
         } else if (n == "frame_queue_depth") {
@@ -458,10 +463,10 @@ ptb_status ptb_scene_clone(const ptb_scene* scene, int device, ptb_scene** out) 
     });
 }
 
-ptb_status ptb_frame_tiling(const ptb_frame_req* req, int world, uint32_t* tile_w, uint32_t* tile_h, uint32_t* n_tiles) {
+ptb_status ptb_frame_tiles(const ptb_frame_req* req, int world, uint32_t* xywh, uint64_t capacity, uint32_t* n_tiles) {
     return guarded([&] {
         if (!req) throw ptb::Error(PTB_E_INVALID, "req is NULL");
-        ptb::frame_tiling(*req, world, tile_w, tile_h, n_tiles);
+        ptb::frame_tiles(*req, world, xywh, capacity, n_tiles);
     });
 }
 

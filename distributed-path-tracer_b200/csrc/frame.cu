@@ -324,12 +324,15 @@ void ensure_frame(ptb_group* g, uint32_t w, uint32_t h) {
     g->frame_h = h;
 }
 
-// Tile grid: the caller's tile size, or one chosen so that every rank has ~24 tiles to steal from while a tile
-// keeps enough paths to fill a GPU launch; multiples of the 64 x 32 pixel super-block of the path order where
-// the frame allows.
+// Tile list, in claim order.  With a tile size from the caller: a uniform grid.  Chosen by the library: a base tile
+// so that every rank has ~24 tiles to steal from while a tile keeps enough paths to fill a launch (multiples of
+// the 32 x 16 pixel granule of the path order) — and, for several ranks, GUIDED scheduling: the first ~60 % of the
+// rows are cut into tiles of 2 x 2 base tiles, which run closer to the GPU's large-wave rate, and only the rest
+// into base tiles, which are what balances the ranks at the end of the frame (big units first, small units last).
 std::vector<Tile> make_tiles(const ptb_frame_req& r, int world) {
     uint32_t tw = r.tile_w, th = r.tile_h;
-    if (tw == 0 || th == 0) {
+    const bool chosen = (tw == 0 || th == 0);
+    if (chosen) {
         const uint64_t want = uint64_t(world) * 24;
         tw = 32;
         th = 16;
@@ -349,19 +352,34 @@ std::vector<Tile> make_tiles(const ptb_frame_req& r, int world) {
     tw = std::min(tw, r.full_w);
     th = std::min(th, r.full_h);
     std::vector<Tile> tiles;
-    for (uint32_t y = 0; y < r.full_h; y += th)
+    uint32_t y0 = 0;
+    if (chosen && world > 1 && g_options.frame_guided_tiles) {
+        const uint32_t bw = std::min(2 * tw, r.full_w), bh = 2 * th;
+        const uint32_t big_rows = uint32_t(uint64_t(r.full_h) * 6 / 10) / bh * bh;
+        for (; y0 < big_rows; y0 += bh)
+            for (uint32_t x = 0; x < r.full_w; x += bw) tiles.push_back(Tile{x, y0, std::min(bw, r.full_w - x), bh});
+    }
+    for (uint32_t y = y0; y < r.full_h; y += th)
         for (uint32_t x = 0; x < r.full_w; x += tw) tiles.push_back(Tile{x, y, std::min(tw, r.full_w - x), std::min(th, r.full_h - y)});
     return tiles;
 }
 
 } // namespace
 
-void frame_tiling(const ptb_frame_req& req, int world, uint32_t* tile_w, uint32_t* tile_h, uint32_t* n_tiles) {
+void frame_tiles(const ptb_frame_req& req, int world, uint32_t* xywh, uint64_t capacity, uint32_t* n_tiles) {
     if (req.full_w == 0 || req.full_h == 0 || world < 1) throw Error(PTB_E_INVALID, "empty frame or bad world size");
+    if (!n_tiles) throw Error(PTB_E_INVALID, "n_tiles is NULL");
     const std::vector<Tile> tiles = make_tiles(req, world);
-    if (tile_w) *tile_w = tiles[0].w;
-    if (tile_h) *tile_h = tiles[0].h;
-    if (n_tiles) *n_tiles = (uint32_t)tiles.size();
+    *n_tiles = (uint32_t)tiles.size();
+    if (xywh) {
+        if (capacity < tiles.size()) throw Error(PTB_E_INVALID, "capacity too small");
+        for (size_t i = 0; i < tiles.size(); i++) {
+            xywh[4 * i] = tiles[i].x0;
+            xywh[4 * i + 1] = tiles[i].y0;
+            xywh[4 * i + 2] = tiles[i].w;
+            xywh[4 * i + 3] = tiles[i].h;
+        }
+    }
 }
 
 // ---- group life cycle ------------------------------------------------------------------------------------------------

@@ -57,6 +57,7 @@ struct LaunchCfg {
     int extend_setup_lanes;         // waiting lanes that trigger the set-up section (variant 1)
     int extend_sm_ranges;           // 1: every SM works through its own contiguous part of the queue first
     int extend_contexts;            // rays per lane of the context kernel (variant 4): 2..4
+    int extend_rays_per_lane;       // blocks beyond ceil(n / (128 x this)) leave at once (0: all blocks stay)
 };
 
 // qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.

@@ -110,6 +110,7 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.extend_setup_lanes = (int)g_options.extend_setup_lanes;
     c.extend_sm_ranges = (int)g_options.extend_sm_ranges;
     c.extend_contexts = (int)g_options.extend_contexts;
+    c.extend_rays_per_lane = (int)g_options.extend_rays_per_lane;
     return c;
 }
 

@@ -20,10 +20,12 @@ struct Options {
     int64_t extend_setup_lanes = 8;             // lanes that must be waiting before the set-up section runs
     int64_t path_order = 1;                     // 1: samples of an 8x4 block adjacent in the queue, 0: sample planes
     int64_t extend_contexts = 2;                // rays per lane of the context kernel (variant 4)
+    int64_t extend_rays_per_lane = 8;           // extend blocks beyond ceil(rays / (128 x this)) exit at once (0 = off)
     int64_t extend_sm_ranges = 0;               // every SM starts on its own contiguous part of the ray queue
     int64_t time_stages = 0;            // CUDA-event pair around every extend / shade launch (perturbs the total)
     int64_t group_timeout_ms = 120000;  // multi-GPU: longest wait at a barrier / rendezvous before PTB_E_NCCL
-    int64_t frame_tiles_in_flight = 6;  // multi-GPU frame: host threads (streams) per GPU
+    int64_t frame_tiles_in_flight = 8;  // multi-GPU frame: host threads (streams) per GPU
+    int64_t frame_guided_tiles = 1;     // library-chosen tiling for several ranks: big tiles first, small tiles last
     int64_t frame_spin_wait = 0;        // workers wait for their tiles by spinning instead of sleeping on a blocking event
     int64_t frame_queue_depth = 1;      // tiles queued per stream (1: claim after the previous tile finished, 2: one ahead)
 };

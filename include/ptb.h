@@ -345,7 +345,7 @@ typedef struct ptb_frame_req {
     uint32_t integrator;              /* ptb_integrator */
     uint32_t first_sample_unjittered;
     uint32_t tile_w, tile_h;          /* the unit of work stealing; 0 = chosen by the library        */
-    uint32_t tiles_in_flight;         /* streams (host threads) per GPU; 0 = default (6)            */
+    uint32_t tiles_in_flight;         /* streams (host threads) per GPU; 0 = default (8)            */
     uint32_t output;                  /* PTB_OUT_*                                                  */
 } ptb_frame_req;
 
@@ -358,9 +358,10 @@ typedef struct ptb_frame_stats {
     double gpu_seconds_per_rank[16];
 } ptb_frame_stats;
 
-/* The tile grid a frame request is cut into for `world` ranks (tile_w / tile_h of the request, or the library's
- * choice when they are 0): row-major, edge tiles absorb the remainder. */
-ptb_status ptb_frame_tiling(const ptb_frame_req* req, int world, uint32_t* tile_w, uint32_t* tile_h, uint32_t* n_tiles);
+/* The tiles a frame request is cut into for `world` ranks, in claim order: (x0, y0, w, h) quadruples.  With
+ * tile_w / tile_h in the request: a uniform row-major grid.  With 0: the library's choice — for several ranks big
+ * tiles first and small tiles last (guided scheduling).  Call with xywh == NULL to obtain the count. */
+ptb_status ptb_frame_tiles(const ptb_frame_req* req, int world, uint32_t* xywh, uint64_t capacity, uint32_t* n_tiles);
 
 /* One process per GPU (torchrun, MPI, ...): collective over `world` processes of ONE node that pass the same
  * `name` (a POSIX shared-memory object "/ptb_<name>": tile counters, barrier, IPC handle of the frame).
@@ -495,7 +496,10 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
  *   "path_order"            1: a wave's samples of one 8x4 pixel block are adjacent in the queue (default);
  *                           0: sample planes
  *   "extend_blocks_per_sm", "shade_blocks_per_sm"   caps on the persistent grids
- *   "frame_tiles_in_flight" multi-GPU frame: streams (host threads) per GPU (default 6)
+ *   "extend_rays_per_lane"  extend blocks beyond ceil(rays / (128 x this)) leave at once, so that a small launch
+ *                           does not hold the whole machine (default 8; 0 = every block stays)
+ *   "frame_tiles_in_flight" multi-GPU frame: streams (host threads) per GPU (default 8)
+ *   "frame_guided_tiles"    library-chosen tiling for several ranks: 1 = big tiles first, small last (default)
  *   "frame_queue_depth"     multi-GPU frame: tiles queued per stream (1 or 2)
  *   "frame_spin_wait"       multi-GPU frame: 1 = workers spin on their tile's event instead of sleeping (default 0)
  *   "group_timeout_ms"      multi-GPU: longest wait at a barrier / rendezvous before PTB_E_NCCL (default 120 000)

@@ -28,12 +28,15 @@ def nvlink_bytes(index):
     seen = False
     for line in out.splitlines():
         line = line.strip()
-        if "Data Rx:" in line:
-            rx += int(line.split("Data Rx:")[1].split()[0]) * 1024
-            seen = True
-        elif "Data Tx:" in line:
-            tx += int(line.split("Data Tx:")[1].split()[0]) * 1024
-            seen = True
+        try:
+            if "Data Rx:" in line:
+                rx += int(line.split("Data Rx:")[1].split()[0]) * 1024
+                seen = True
+            elif "Data Tx:" in line:
+                tx += int(line.split("Data Tx:")[1].split()[0]) * 1024
+                seen = True
+        except ValueError:  # "N/A": the counters are not exposed in this container
+            return None
     return (rx, tx) if seen else None
 
 
@@ -61,9 +64,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(tile, streams, depth_q, to_host, spin=0):
+    def run(tile, streams, depth_q, to_host, spin=0, rpl=None):
         ptb.set_option("frame_queue_depth", depth_q)
         ptb.set_option("frame_spin_wait", spin)
+        if rpl is not None:
+            ptb.set_option("extend_rays_per_lane", rpl)
         out = pinned.data_ptr() if (to_host and rank == 0) else None
         kw = dict(seed=1, tile=tile, tiles_in_flight=streams, output=ptb.OUT_RGBA32F if to_host else ptb.OUT_NONE)
         for i in range(2):
@@ -85,11 +90,21 @@ def main():
         if rank == 0:
             per = np.array(st["gpu_seconds_per_rank"]) * 1e3
             print(json.dumps(dict(world=world, tile=list(tile), n_tiles=st["n_tiles"], streams=streams, queue_depth=depth_q,
-                                  spin=spin, to_host=to_host, gpu_ms=round(gpu / steps, 3), wall_ms=round(wall / steps, 3),
+                                  spin=spin, rays_per_lane=rpl, to_host=to_host, gpu_ms=round(gpu / steps, 3), wall_ms=round(wall / steps, 3),
                                   mrays_s=round(rays / (gpu * 1e-3) / 1e6, 1), frames_s_wall=round(1e3 / (wall / steps), 2),
                                   tiles_per_rank=st["tiles_per_rank"], last_gpu_ms_per_rank=[round(float(x), 2) for x in per])),
                   flush=True)
 
+    if os.environ.get("SWEEP_SETTINGS"):
+        # explicit list: [[tile_w, tile_h, streams, queue_depth, spin, rays_per_lane], ...]
+        for tw, th, streams, dq, spin, rpl in json.loads(os.environ["SWEEP_SETTINGS"]):
+            run((tw, th), streams, dq, False, spin=spin, rpl=rpl)
+        group.barrier()
+        group.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     settings = [((0, 0), 6, 1)]
     if os.environ.get("SWEEP_FULL", "1") != "0":
         for tile in ((0, 0), (128, 64), (192, 96), (256, 128), (96, 48), (320, 160)):
