@@ -256,6 +256,9 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "extend_setup_lanes") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_setup_lanes must be 1..32");
             ptb::g_options.extend_setup_lanes = value;
+        } else if (n == "extend_test_lanes") {
+            if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_test_lanes must be 1..32");
+            ptb::g_options.extend_test_lanes = value;
         } else if (n == "path_order") {
             ptb::g_options.path_order = value != 0;
         } else if (n == "extend_contexts") {

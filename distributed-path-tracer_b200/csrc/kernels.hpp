@@ -55,6 +55,7 @@ struct LaunchCfg {
     int extend_variant; // 0: one thread per ray (kernels.cu), 1: lane state machine (extend.cu)
     int extend_steps, extend_tests; // node steps / triangle tests offered per main-loop iteration (variant 1)
     int extend_setup_lanes;         // waiting lanes that trigger the set-up section (variant 1)
+    int extend_test_lanes;          // lanes waiting in a leaf that trigger a triangle-test slot
     int extend_sm_ranges;           // 1: every SM works through its own contiguous part of the queue first
     int extend_contexts;            // rays per lane of the context kernel (variant 4): 2..4
     int extend_rays_per_lane;       // blocks beyond ceil(n / (128 x this)) leave at once (0: all blocks stay)

@@ -108,6 +108,7 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.extend_steps = (int)g_options.extend_steps;
     c.extend_tests = (int)g_options.extend_tests;
     c.extend_setup_lanes = (int)g_options.extend_setup_lanes;
+    c.extend_test_lanes = (int)g_options.extend_test_lanes;
     c.extend_sm_ranges = (int)g_options.extend_sm_ranges;
     c.extend_contexts = (int)g_options.extend_contexts;
     c.extend_rays_per_lane = (int)g_options.extend_rays_per_lane;

@@ -18,6 +18,7 @@ struct Options {
     int64_t extend_variant = 1;         // 0: one thread per ray, 1: lane state machine with ray replacement
     int64_t extend_steps = 4, extend_tests = 2; // work offered per main-loop iteration of the lane kernel
     int64_t extend_setup_lanes = 8;             // lanes that must be waiting before the set-up section runs
+    int64_t extend_test_lanes = 1;              // lanes that must wait in a leaf before a triangle-test slot is offered
     int64_t path_order = 1;                     // 1: samples of an 8x4 block adjacent in the queue, 0: sample planes
     int64_t extend_contexts = 2;                // rays per lane of the context kernel (variant 4)
     int64_t extend_rays_per_lane = 8;           // extend blocks beyond ceil(rays / (128 x this)) exit at once (0 = off)
