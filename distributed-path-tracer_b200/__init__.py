@@ -23,7 +23,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libptb.so")
+SO_PATH = os.environ.get("PTB_LIB") or os.path.join(HERE, "libptb.so")  # PTB_LIB: A/B builds of the same library
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "ptb.h")
 
 PTB_OK, PTB_E_INVALID, PTB_E_CUDA, PTB_E_NCCL, PTB_E_OOM, PTB_E_IO = range(6)
@@ -270,6 +270,12 @@ def lib():
     L.ptb_group_selftest_host.restype = st
     L.ptb_group_selftest_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     _lib = L
+    # A/B runs of whole test suites / benches: PTB_OPTIONS="extend_defer=0,extend_setup_lanes=12"
+    for item in filter(None, os.environ.get("PTB_OPTIONS", "").split(",")):
+        name, _, value = item.partition("=")
+        st_ = L.ptb_set_option(name.strip().encode(), int(value))
+        if st_ != PTB_OK:
+            raise PtbError(st_, f"PTB_OPTIONS: {item!r}: " + L.ptb_last_error().decode("utf-8", "replace"))
     return L
 
 

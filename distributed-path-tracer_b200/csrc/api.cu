@@ -256,9 +256,9 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "extend_setup_lanes") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_setup_lanes must be 1..32");
             ptb::g_options.extend_setup_lanes = value;
-        } else if (n == "extend_test_lanes") {
-            if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_test_lanes must be 1..32");
-            ptb::g_options.extend_test_lanes = value;
+        } else if (n == "extend_defer") {
+            if (value < 0 || value > 1) throw ptb::Error(PTB_E_INVALID, "extend_defer must be 0 or 1");
+            ptb::g_options.extend_defer = value;
         } else if (n == "path_order") {
             ptb::g_options.path_order = value != 0;
         } else if (n == "extend_contexts") {
@@ -570,7 +570,7 @@ int ptb_extend_registers(void) {
     if (ptb::g_options.extend_variant == 4) return ptb::extend_ctx_regs_per_thread((int)ptb::g_options.extend_contexts);
     if (ptb::g_options.extend_variant == 0) return ptb::extend_regs_per_thread();
 #endif
-    return ptb::extend_lanes_regs_per_thread();
+    return ptb::extend_lanes_regs_per_thread(ptb::g_options.extend_defer != 0);
 }
 int ptb_shadow_registers(void) { return ptb::extend_anyhit_regs_per_thread(); }
 uint64_t ptb_selftest_division(uint64_t n, uint64_t seed) { return ptb::division_selftest(n, seed); }

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(T_THREADS, MINB)
                     if (st == CS_TRAV && (nd.y & 3u) != 3u) {
                         if (COUNT) c_nodes++;
                         // both children in one aligned 16-byte load, in flight during the arithmetic below
-                        const uint4 ch = __ldg(S.kd_pairs + (nd.y >> 3));
+                        const uint4 ch = __ldg(S.kd_pairs + (nd.y >> 2));
                         const uint32_t axis = nd.y & 3u;
                         const float split = __uint_as_float(nd.x);
                         float oa, da, ya;

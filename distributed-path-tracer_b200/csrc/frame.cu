@@ -131,6 +131,7 @@ struct ptb_group {
     float4* job_frame = nullptr;
     int job_depth = 1;
     bool job_spin = false;
+    uint32_t job_max_w = 0, job_max_h = 0; // the largest tile of the frame: every worker's buffers are sized for it
     std::string job_error;
     ptb_status job_status = PTB_OK;
 };
@@ -190,6 +191,7 @@ void worker_main(ptb_group* g, ptb_group::Worker* w, int index) {
             const ptb_frame_req& fr = g->job_req;
             const std::vector<Tile>& tiles = *g->job_tiles;
             const uint32_t n_tiles = (uint32_t)tiles.size();
+            reserve_tile_workspace(g->job_scene, w->st, g->job_max_w, g->job_max_h, fr.spp, fr.max_depth);
             PTB_CUDA(cudaStreamWaitEvent(w->st, g->ev_start, 0));
             stream_counters_reset(g->device, w->st);
             bool outstanding[2] = {false, false};
@@ -572,6 +574,11 @@ void group_render_frame(ptb_group* g, const ptb_scene* scene, const ptb_frame_re
         g->job_tiles = &tiles;
         g->job_counter = &sh->counter[e & 1u];
         g->job_frame = frame;
+        g->job_max_w = g->job_max_h = 0;
+        for (const Tile& t : tiles) { // (the padded size is monotone in both dimensions)
+            g->job_max_w = std::max(g->job_max_w, t.w);
+            g->job_max_h = std::max(g->job_max_h, t.h);
+        }
         g->job_depth = g_options.frame_queue_depth >= 2 ? 2 : 1;
         g->job_spin = g_options.frame_spin_wait != 0;
         g->job_status = PTB_OK;

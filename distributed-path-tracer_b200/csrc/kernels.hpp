@@ -55,7 +55,7 @@ struct LaunchCfg {
     int extend_variant; // 0: one thread per ray (kernels.cu), 1: lane state machine (extend.cu)
     int extend_steps, extend_tests; // node steps / triangle tests offered per main-loop iteration (variant 1)
     int extend_setup_lanes;         // waiting lanes that trigger the set-up section (variant 1)
-    int extend_test_lanes;          // lanes waiting in a leaf that trigger a triangle-test slot
+    int extend_defer;               // 1: leaves are registered and tested while the lane keeps descending (extend.cu: DEFER)
     int extend_sm_ranges;           // 1: every SM works through its own contiguous part of the queue first
     int extend_contexts;            // rays per lane of the context kernel (variant 4): 2..4
     int extend_rays_per_lane;       // blocks beyond ceil(n / (128 x this)) leave at once (0: all blocks stay)
@@ -125,7 +125,7 @@ void launch_extend_lanes_merge(const DScene& S, const float4* ray_o, const float
 void launch_extend_anyhit(const DScene& S, const float4* ray_o, const float4* ray_d, uint8_t* occluded,
                           const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
                           cudaStream_t st);
-int extend_lanes_regs_per_thread();
+int extend_lanes_regs_per_thread(bool defer);
 int extend_anyhit_regs_per_thread();
 
 // ---- experiments (csrc/experiments/, built only with PTB_BUILD_EXPERIMENTS=1; option extend_variant) ----

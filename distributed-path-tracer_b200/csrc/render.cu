@@ -108,7 +108,7 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.extend_steps = (int)g_options.extend_steps;
     c.extend_tests = (int)g_options.extend_tests;
     c.extend_setup_lanes = (int)g_options.extend_setup_lanes;
-    c.extend_test_lanes = (int)g_options.extend_test_lanes;
+    c.extend_defer = (int)g_options.extend_defer;
     c.extend_sm_ranges = (int)g_options.extend_sm_ranges;
     c.extend_contexts = (int)g_options.extend_contexts;
     c.extend_rays_per_lane = (int)g_options.extend_rays_per_lane;
@@ -121,6 +121,51 @@ struct TileTarget {
     uint8_t* claimed; // caller-owned claim mask (w*h bytes) or null
 };
 
+// Paths of one wave of a w x h tile and the buffers that hold them.
+struct TileSizing {
+    WaveGeom g{};
+    uint64_t wave_samples = 1, cap = 0;
+};
+
+TileSizing size_tile(uint32_t w, uint32_t h, uint32_t spp) {
+    TileSizing z;
+    WaveGeom& g = z.g;
+    g.w = w;
+    g.h = h;
+    g.blocks_x = (w + 7) / 8;
+    g.blocks_y = (h + 3) / 4;
+    g.sblocks_x = (g.blocks_x + 7) / 8;
+    g.block_major = g_options.path_order != 0;
+    const uint64_t padded = uint64_t(g.sblocks_x) * ((g.blocks_y + 7) / 8) * 64 * 32;
+    if (padded >= (1ull << 31)) throw Error(PTB_E_INVALID, "tile too large");
+    g.padded_pixels = (uint32_t)padded;
+    uint64_t wave_samples = std::max<uint64_t>(1, (uint64_t)g_options.wave_paths / padded);
+    wave_samples = std::min<uint64_t>(wave_samples, std::max<uint32_t>(spp, 1));
+    while (wave_samples > 1 && wave_samples * padded >= (1ull << 32)) wave_samples--;
+    z.wave_samples = wave_samples;
+    z.cap = wave_samples * padded;
+    return z;
+}
+
+// Every device buffer a tile of this size needs (a cudaMalloc synchronises the whole device: inside a frame with
+// several tiles in flight it would stall all of them, so the frame driver sizes the workspaces up front).
+void ensure_tile_buffers(Workspace& w, const TileSizing& z, uint32_t max_depth, bool sun, bool transparent, uint32_t tw,
+                         uint32_t th) {
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 4; j++) w.path[i][j].ensure(z.cap * sizeof(float4));
+    w.hits.ensure(z.cap * sizeof(uint4));
+    w.sample_out.ensure(z.cap * sizeof(float4));
+    const size_t n_counters = size_t(max_depth) + MAX_EXTRA_ITERS + 2;
+    w.qcount.ensure(n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t) * (sun ? 2 : 1));
+    if (sun) {
+        w.sh_o.ensure(z.cap * sizeof(float4));
+        w.sh_d.ensure(z.cap * sizeof(float4));
+        w.sh_slot.ensure(z.cap * sizeof(uint32_t));
+        w.sh_occluded.ensure(z.cap);
+    }
+    if (transparent) w.claimed.ensure(size_t(tw) * th);
+}
+
 // The wavefront loop for one tile.  The caller holds w.lock.
 //   dst        where the running mean lives: pixel (0,0) of the tile inside a buffer with dst.pitch pixels per
 //              row (the caller's tile buffer, or a full frame — possibly peer-mapped memory of another GPU)
@@ -131,20 +176,11 @@ void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& re
                         ptb_render_stats* stats) {
     w.events();
 
-    WaveGeom g{};
+    const TileSizing sizing = size_tile(req.w, req.h, req.spp);
+    WaveGeom g = sizing.g;
     g.full_w = req.full_w; g.full_h = req.full_h;
-    g.x0 = req.x0; g.y0 = req.y0; g.w = req.w; g.h = req.h;
-    g.blocks_x = (req.w + 7) / 8;
-    g.blocks_y = (req.h + 3) / 4;
-    g.sblocks_x = (g.blocks_x + 7) / 8;
-    g.block_major = g_options.path_order != 0;
-    const uint64_t padded = uint64_t(g.sblocks_x) * ((g.blocks_y + 7) / 8) * 64 * 32;
-    if (padded >= (1ull << 31)) throw Error(PTB_E_INVALID, "tile too large");
-    g.padded_pixels = (uint32_t)padded;
-    uint64_t wave_samples = std::max<uint64_t>(1, (uint64_t)g_options.wave_paths / padded);
-    wave_samples = std::min<uint64_t>(wave_samples, std::max<uint32_t>(req.spp, 1));
-    while (wave_samples > 1 && wave_samples * padded >= (1ull << 32)) wave_samples--;
-    const uint64_t cap = wave_samples * padded;
+    g.x0 = req.x0; g.y0 = req.y0;
+    const uint64_t wave_samples = sizing.wave_samples;
 
     RenderParams rp{};
     rp.seed_lo = (uint32_t)req.seed;
@@ -153,21 +189,11 @@ void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& re
     rp.integrator = req.integrator;
     rp.first_sample_unjittered = req.first_sample_unjittered;
 
-    for (int i = 0; i < 2; i++)
-        for (int j = 0; j < 4; j++) w.path[i][j].ensure(cap * sizeof(float4));
-    w.hits.ensure(cap * sizeof(uint4));
-    w.sample_out.ensure(cap * sizeof(float4));
     const uint32_t n_iters_fixed = req.max_depth;
     const size_t n_counters = size_t(n_iters_fixed) + MAX_EXTRA_ITERS + 2;
     const bool sun = s->d.sun.enabled != 0;
     // per iteration: queue size + extend's work heads; with a sun the same again for the shadow queue
-    w.qcount.ensure(n_counters * (1 + QHEAD_STRIDE) * sizeof(uint32_t) * (sun ? 2 : 1));
-    if (sun) {
-        w.sh_o.ensure(cap * sizeof(float4));
-        w.sh_d.ensure(cap * sizeof(float4));
-        w.sh_slot.ensure(cap * sizeof(uint32_t));
-        w.sh_occluded.ensure(cap);
-    }
+    ensure_tile_buffers(w, sizing, req.max_depth, sun, false, req.w, req.h);
     if (!w.counters.p) {
         w.counters.ensure(sizeof(DeviceCounters));
         PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
@@ -325,6 +351,13 @@ void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, float4* base,
     Workspace& w = workspace(s->device, st);
     std::lock_guard<std::mutex> guard(w.lock);
     render_tile_locked(w, s, req, TileTarget{base, pitch, nullptr}, st, nullptr);
+}
+
+void reserve_tile_workspace(const ptb_scene* s, cudaStream_t st, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth) {
+    Workspace& ws = workspace(s->device, st);
+    std::lock_guard<std::mutex> guard(ws.lock);
+    ensure_tile_buffers(ws, size_tile(w, h, spp), max_depth, s->d.sun.enabled != 0, s->d.transparent_background != 0, w, h);
+    ws.counters.ensure(sizeof(DeviceCounters));
 }
 
 void stream_counters_reset(int device, cudaStream_t st) {

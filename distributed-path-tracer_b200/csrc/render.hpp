@@ -18,7 +18,7 @@ struct Options {
     int64_t extend_variant = 1;         // 0: one thread per ray, 1: lane state machine with ray replacement
     int64_t extend_steps = 4, extend_tests = 2; // work offered per main-loop iteration of the lane kernel
     int64_t extend_setup_lanes = 8;             // lanes that must be waiting before the set-up section runs
-    int64_t extend_test_lanes = 1;              // lanes that must wait in a leaf before a triangle-test slot is offered
+    int64_t extend_defer = 1;                   // 1: leaves are registered and tested while the lane keeps descending
     int64_t path_order = 1;                     // 1: samples of an 8x4 block adjacent in the queue, 0: sample planes
     int64_t extend_contexts = 2;                // rays per lane of the context kernel (variant 4)
     int64_t extend_rays_per_lane = 8;           // extend blocks beyond ceil(rays / (128 x this)) exit at once (0 = off)
@@ -39,6 +39,8 @@ void render_tile_host(const ptb_scene* s, const ptb_tile_req& req, float* rgb_ou
 // frame driver: one tile accumulated in place at `base` (pitch pixels per row, own or peer-mapped memory),
 // asynchronous on `st`; rays / paths / launches add up in the stream's workspace until they are read
 void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, float4* base, uint32_t pitch, cudaStream_t st);
+// sizes the stream's workspace for w x h tiles before a frame starts (no allocation inside the frame)
+void reserve_tile_workspace(const ptb_scene* s, cudaStream_t st, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth);
 void stream_counters_reset(int device, cudaStream_t st);
 void stream_counters_read(int device, cudaStream_t st, uint64_t* rays, uint64_t* paths, uint64_t* launches);
 void trace_rays_host(const ptb_scene* s, const float* origin_dir, uint64_t n, ptb_hit* hits_out, float* attrs_out,

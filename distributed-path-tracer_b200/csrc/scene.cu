@@ -98,35 +98,31 @@ void require(bool ok, const char* msg) {
     if (!ok) throw Error(PTB_E_INVALID, msg);
 }
 
-// The traversal kernel's view of a tree: SIBLING PAIRS in TREELET BLOCKS.  One 16-byte pair holds the records of
-// both children of a branch (left in .xy, right in .zw), so a step fetches both with a single aligned load, and
-// the record of the far child can go onto the traversal stack (a pop needs no further load).  A record is
-//   branch  x = split plane (float bits)      y = axis (0..2) | dbl << 2 | child pair index << 3   (index into kd_pairs)
+// The traversal kernel's view of a tree: SIBLING PAIRS.  One 16-byte element holds the records of both
+// children of a branch (left in .xy, right in .zw), so a step fetches both with a single aligned load that
+// does not depend on the step's arithmetic, and the record of the far child can go onto the traversal
+// stack (a pop needs no further load).  A record is
+//   branch  x = split plane (float bits)      y = axis (0..2) | child pair index << 2   (index into kd_pairs)
 //   leaf    x = first reference (index into kd_refs)   y = 3 | count << 2
 //   absent  x = 0                             y = 3           (the reference's null child, mesh.cpp:372)
 // Indices are ABSOLUTE (all meshes share the arrays), so the kernel carries no per-mesh base for them.
-// Pairs are laid out in blocks of three (48 bytes): a branch N on an EVEN level of its tree owns a block
-//   [ children of N | children of N.left | children of N.right ]
-// and carries dbl = 1: the traversal knows which child it will descend to BEFORE it loads anything (the decision
-// needs only N's own plane and the ray), so it requests N's pair and that child's pair together — two levels of
-// the tree per memory round trip instead of one.  A branch on an odd level finds its children in its parent's block
-// (dbl = 0: its grandchildren live in the blocks of its children).  The first pair of a mesh (DMesh::pair_base)
-// carries the root (level 0) in .xy.  Same tree, same order of children: nothing about the traversal's decisions
-// changes.  Depth-first, left subtree first, so a descent to the left stays in a line.
+// The first pair of a mesh (DMesh::pair_base) carries the root in .xy.  Same tree, same order of children: nothing about the
+// traversal's decisions changes.  Depth-first, left subtree first, so a descent to the left stays in a line.
+// (Round 2 tried blocks of three pairs — a branch on an even level next to both of its children's pairs, so that two
+// tree levels could be requested per round trip: the two-level step and the 50 % larger pair array cost 8 % on C2.)
 constexpr uint32_t KD_ABSENT_Y = KD_LEAF_TAG;
 
 void append_sibling_pairs(const KdTree& tree, uint32_t ref_base, std::vector<uint4>& pairs) {
-    const uint4 empty = make_uint4(0, KD_ABSENT_Y, 0, KD_ABSENT_Y);
-    pairs.push_back(empty); // the root's record goes into .xy
+    const size_t base = pairs.size();
+    pairs.push_back(make_uint4(0, KD_ABSENT_Y, 0, KD_ABSENT_Y));
     if (tree.nodes.empty()) return;
     struct Item {
-        uint32_t src;        // index in tree.nodes
-        uint32_t pair;       // destination pair (absolute)
-        uint32_t half;       // 0: .xy, 1: .zw
-        uint32_t child_pair; // odd level: where this node's children go (inside the parent's block); 0 = even level
+        uint32_t src;  // index in tree.nodes
+        uint32_t pair; // destination pair (mesh-relative)
+        uint32_t half; // 0: .xy, 1: .zw
     };
     std::vector<Item> todo;
-    todo.push_back(Item{0, static_cast<uint32_t>(pairs.size() - 1), 0, 0});
+    todo.push_back(Item{0, 0, 0});
     while (!todo.empty()) {
         const Item it = todo.back();
         todo.pop_back();
@@ -134,23 +130,16 @@ void append_sibling_pairs(const KdTree& tree, uint32_t ref_base, std::vector<uin
         uint32_t x = n.w0, y = n.w1;
         if ((n.w1 & 3u) != KD_LEAF_TAG) {
             const uint32_t has_l = (n.w1 >> 2) & 1u, has_r = (n.w1 >> 3) & 1u, first = n.w1 >> 4;
-            if (it.child_pair == 0) { // even level: a new block; the children are on an odd level
-                const uint32_t block = static_cast<uint32_t>(pairs.size());
-                pairs.push_back(empty);
-                pairs.push_back(empty);
-                pairs.push_back(empty);
-                y = (n.w1 & 3u) | 4u | (block << 3);
-                if (has_r) todo.push_back(Item{first + has_l, block, 1, block + 2});
-                if (has_l) todo.push_back(Item{first, block, 0, block + 1}); // popped next: left subtree first
-            } else { // odd level: the children pair is the slot the parent's block reserved
-                y = (n.w1 & 3u) | (it.child_pair << 3);
-                if (has_r) todo.push_back(Item{first + has_l, it.child_pair, 1, 0});
-                if (has_l) todo.push_back(Item{first, it.child_pair, 0, 0});
-            }
+            const uint32_t child_pair = static_cast<uint32_t>(pairs.size());
+            pairs.push_back(make_uint4(0, KD_ABSENT_Y, 0, KD_ABSENT_Y));
+            y = (n.w1 & 3u) | (child_pair << 2);
+            const uint32_t rel = child_pair - static_cast<uint32_t>(base);
+            if (has_r) todo.push_back(Item{first + has_l, rel, 1});
+            if (has_l) todo.push_back(Item{first, rel, 0}); // popped next: left subtree first
         } else {
             x = n.w0 + ref_base;
         }
-        uint4& dst = pairs[it.pair];
+        uint4& dst = pairs[base + it.pair];
         if (it.half == 0) {
             dst.x = x;
             dst.y = y;

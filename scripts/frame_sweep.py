@@ -55,7 +55,7 @@ def main():
     scene = ptb.Scene.create(P.heightfield_scene(n_grid), local) if rank == 0 else None
     scene = cluster.replicate_scene(scene, local)
     group = cluster.make_group(local)
-    W, H, spp, depth = 1920, 1080, 64, 4
+    W, H, spp, depth = int(os.environ.get("SWEEP_W", "1920")), int(os.environ.get("SWEEP_H", "1080")), 64, 4
     pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
     steps = int(os.environ.get("SWEEP_STEPS", "6"))
 
