@@ -413,9 +413,13 @@ def run_ptb(args):
 
     if rank == 0:
         frames_per_s = 1e3 / main["ms_per_step"] * (world if weak else 1)
-        tl = ptb.frame_tiles(full_w, full_h, spp_main, world, tile)
-        tile_desc = f"{tl[0][2]}x{tl[0][3]}" + (f" first, {tl[-len(tl) // 3][2]}x{tl[-len(tl) // 3][3]} last (guided)"
-                                                if tl[0][2:] != tl[-len(tl) // 3][2:] else "")
+        tl = ptb.frame_tile_layout(full_w, full_h, spp_main, world, tile, tiles_in_flight=args.streams).tolist()
+        if tl[0][4]:  # comb tiles: granules of gx x gy pixels spread over the whole frame, all tiles equal
+            tile_desc = (f"{tl[0][2]}x{tl[0][3]} pixels each, as {tl[0][4]}x{tl[0][6]}-pixel granules "
+                         f"{tl[0][5]}x{tl[0][7]} apart (comb tiles: every tile samples the whole frame)")
+        else:
+            tile_desc = f"{tl[0][2]}x{tl[0][3]}" + (f" first, {tl[-len(tl) // 3][2]}x{tl[-len(tl) // 3][3]} last (guided)"
+                                                    if tl[0][2:4] != tl[-len(tl) // 3][2:4] else "")
         line = {
             "metric": "Mrays/s", "value": main["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
@@ -426,7 +430,9 @@ def run_ptb(args):
                        "kd_build_s": t_build, "scene_replicate_s": t_replicate if world > 1 else None,
                        "scene_replication": "built once on rank 0; flattened blob broadcast over NCCL" if world > 1 else None,
                        "tiles": f"{n_tiles_main} tiles of {tile_desc}, stolen from one shared counter, "
-                                f"{args.streams or 8} in flight per GPU",
+                                + (f"{args.streams} in flight per GPU" if args.streams else
+                                   (f"{n_tiles_main // world} per GPU (library's choice of tiles in flight: 3..8 of ~4 M paths)"
+                                    if tl[0][4] else "8 in flight per GPU")),
                        "tiles_per_rank": main["tiles_per_rank"],
                        "frame_return": "accumulate kernels store into rank 0's frame over NVLink (CUDA IPC), inside the timed region",
                        "parallelism": f"tiles x{world}", "wave_paths": args.wave_paths,

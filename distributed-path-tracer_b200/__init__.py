@@ -153,7 +153,7 @@ EXPORTS = [
     "ptb_scene_blob", "ptb_scene_export_header", "ptb_scene_import", "ptb_scene_clone",
     "ptb_group_create", "ptb_group_destroy", "ptb_group_barrier", "ptb_group_render_frame",
     "ptb_ctx_create", "ptb_ctx_destroy", "ptb_ctx_set_scene", "ptb_ctx_load_gltf", "ptb_ctx_scene", "ptb_render_frame",
-    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host", "ptb_frame_tiles", "ptb_shadow_registers", "ptb_trace_occlusion",
+    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host", "ptb_frame_tiles", "ptb_frame_tile_layout", "ptb_shadow_registers", "ptb_trace_occlusion",
 ]
 
 _lib = None
@@ -267,6 +267,8 @@ def lib():
     L.ptb_host_free.argtypes = [C.c_void_p]
     L.ptb_frame_tiles.restype = st
     L.ptb_frame_tiles.argtypes = [C.POINTER(FrameReq), C.c_int, u32p, C.c_uint64, u32p]
+    L.ptb_frame_tile_layout.restype = st
+    L.ptb_frame_tile_layout.argtypes = [C.POINTER(FrameReq), C.c_int, u32p, C.c_uint64, u32p]
     L.ptb_group_selftest_host.restype = st
     L.ptb_group_selftest_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     _lib = L
@@ -639,6 +641,25 @@ def frame_tiles(full_w, full_h, spp, world=1, tile=(0, 0)):
     xywh = np.zeros((n.value, 4), np.uint32)
     _check(lib().ptb_frame_tiles(C.byref(req), world, _up(xywh), n.value, C.byref(n)))
     return [tuple(int(v) for v in t) for t in xywh]
+
+
+def frame_tile_layout(full_w, full_h, spp, world=1, tile=(0, 0), tiles_in_flight=0):
+    """→ uint32[n, 8]: (x0, y0, w, h, gx, sx, gy, sy) per tile (include/ptb.h: ptb_frame_tile_layout)."""
+    req = _frame_req(full_w, full_h, spp, 1, tile=tile, tiles_in_flight=tiles_in_flight)
+    n = C.c_uint32()
+    _check(lib().ptb_frame_tile_layout(C.byref(req), world, None, 0, C.byref(n)))
+    out = np.zeros((n.value, 8), np.uint32)
+    _check(lib().ptb_frame_tile_layout(C.byref(req), world, _up(out), n.value, C.byref(n)))
+    return out
+
+
+def tile_pixels(layout_row):
+    """Frame pixels (xs, ys) a tile of frame_tile_layout covers: the tile is their outer product."""
+    x0, y0, w, h, gx, sx, gy, sy = (int(v) for v in layout_row)
+    x, y = np.arange(w), np.arange(h)
+    xs = x0 + ((x // gx) * sx + x % gx if gx else x)
+    ys = y0 + ((y // gy) * sy + y % gy if gy else y)
+    return xs, ys
 
 
 def _frame_out(req: FrameReq, out):

@@ -256,6 +256,12 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "extend_setup_lanes") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_setup_lanes must be 1..32");
             ptb::g_options.extend_setup_lanes = value;
+        } else if (n == "frame_comb_tiles") {
+            if (value < 0 || value > 2) throw ptb::Error(PTB_E_INVALID, "frame_comb_tiles must be 0, 1 or 2");
+            ptb::g_options.frame_comb_tiles = value;
+        } else if (n == "frame_comb_rounds") {
+            if (value < 0 || value > 64) throw ptb::Error(PTB_E_INVALID, "frame_comb_rounds must be 0..64");
+            ptb::g_options.frame_comb_rounds = value;
         } else if (n == "extend_defer") {
             if (value < 0 || value > 1) throw ptb::Error(PTB_E_INVALID, "extend_defer must be 0 or 1");
             ptb::g_options.extend_defer = value;
@@ -469,7 +475,14 @@ ptb_status ptb_scene_clone(const ptb_scene* scene, int device, ptb_scene** out) 
 ptb_status ptb_frame_tiles(const ptb_frame_req* req, int world, uint32_t* xywh, uint64_t capacity, uint32_t* n_tiles) {
     return guarded([&] {
         if (!req) throw ptb::Error(PTB_E_INVALID, "req is NULL");
-        ptb::frame_tiles(*req, world, xywh, capacity, n_tiles);
+        ptb::frame_tiles(*req, world, xywh, capacity, n_tiles, false);
+    });
+}
+
+ptb_status ptb_frame_tile_layout(const ptb_frame_req* req, int world, uint32_t* layout, uint64_t capacity, uint32_t* n_tiles) {
+    return guarded([&] {
+        if (!req) throw ptb::Error(PTB_E_INVALID, "req is NULL");
+        ptb::frame_tiles(*req, world, layout, capacity, n_tiles, true);
     });
 }
 

@@ -24,6 +24,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
@@ -72,6 +73,7 @@ struct GroupShared {
 
 struct Tile {
     uint32_t x0, y0, w, h;
+    TileComb comb; // all 0: a rectangle
 };
 
 double now_seconds() {
@@ -221,7 +223,7 @@ void worker_main(ptb_group* g, ptb_group::Worker* w, int index) {
                 tr.integrator = fr.integrator;
                 tr.first_sample_unjittered = fr.first_sample_unjittered;
                 // straight into the frame on rank 0's GPU: base = the tile's first pixel, pitch = the frame's width
-                render_tile_into(g->job_scene, tr, g->job_frame + size_t(t.y0) * fr.full_w + t.x0, fr.full_w, w->st);
+                render_tile_into(g->job_scene, tr, t.comb, g->job_frame + size_t(t.y0) * fr.full_w + t.x0, fr.full_w, w->st);
                 PTB_CUDA(cudaEventRecord(done[slot], w->st));
                 outstanding[slot] = true;
                 slot = (slot + 1) % g->job_depth;
@@ -326,14 +328,91 @@ void ensure_frame(ptb_group* g, uint32_t w, uint32_t h) {
     g->frame_h = h;
 }
 
+// Pixels one comb phase covers along an axis: granules c, c + C, c + 2C, ... of G pixels (the frame's last granule
+// may be partial).
+uint32_t comb_extent(uint32_t full, uint32_t G, uint32_t C, uint32_t c) {
+    const uint32_t n_gran = (full + G - 1) / G;
+    if (c >= n_gran) return 0;
+    const uint32_t mine = (n_gran - 1 - c) / C + 1;
+    const uint32_t last = c + (mine - 1) * C;
+    return (mine - 1) * G + (last == n_gran - 1 ? full - last * G : G);
+}
+
+// COMB tiles, the library's choice for several ranks.  A fixed frame cut over N GPUs leaves each of them little work
+// (1080p x 64 spp over 8 B200s: 26 ms), and a GPU is only fast on LARGE launches — while rectangular tiles of very
+// different cost (sky against terrain) need to be SMALL to balance the ranks at the end of the frame.  A comb tile is
+// both large and average: tile (c, p) of C x P holds the pixel granules (c + i C, p + j P) of the whole frame, so
+// every tile samples the entire image and all tiles cost the same (to the granule count: < 1 %).  N x in-flight x rounds
+// tiles: every stream of every rank renders `rounds` tiles of full launch size, and all finish together.  Which rank
+// takes which tile still does not matter (shared counter), and the pixels do not depend on the tiling at all.
+std::vector<Tile> make_comb_tiles(const ptb_frame_req& r, uint32_t T) {
+    const uint64_t npix = uint64_t(r.full_w) * r.full_h;
+    static const uint32_t GX[] = {64, 32, 16, 8}, GY[] = {32, 16, 8, 4}; // whole 8 x 4 pixel blocks (a warp's bundle of primary rays)
+    // pass 1: the smallest "largest tile" any comb achieves; pass 2: among the combs within 1 % of it, the one with
+    // the largest granules and the squarest shape (rays of neighbouring blocks share tree nodes in L1 / L2)
+    uint64_t min_worst = ~0ull, best_penalty = ~0ull;
+    uint32_t bC = 0, bP = 0, bgx = 0, bgy = 0;
+    for (int pass = 0; pass < 2; pass++)
+        for (uint32_t C = 1; C <= T; C++) {
+            if (T % C) continue;
+            const uint32_t P = T / C;
+            for (uint32_t gx : GX)
+                for (uint32_t gy : GY) {
+                    if (uint64_t(C) * gx > r.full_w || uint64_t(P) * gy > r.full_h) continue; // every phase needs a granule
+                    // (phase 0 is never smaller than another phase)
+                    const uint64_t worst = uint64_t(comb_extent(r.full_w, gx, C, 0)) * comb_extent(r.full_h, gy, P, 0);
+                    if (pass == 0) {
+                        min_worst = std::min(min_worst, worst);
+                    } else if (worst <= min_worst + min_worst / 100) {
+                        const uint64_t penalty = (64 / gx) * (32 / gy) * 16 + (C > P ? C / P : P / C);
+                        if (penalty < best_penalty) {
+                            best_penalty = penalty;
+                            bC = C; bP = P; bgx = gx; bgy = gy;
+                        }
+                    }
+                }
+        }
+    std::vector<Tile> tiles;
+    // no even comb, or tiles too small to be worth a launch of their own (a tiny frame): rectangles
+    if (!bC || min_worst * T > npix + npix / 8) return tiles;
+    if (g_options.frame_comb_tiles != 2 && min_worst * std::max<uint32_t>(r.spp, 1) < (64u << 10)) return tiles;
+    for (uint32_t p = 0; p < bP; p++)
+        for (uint32_t c = 0; c < bC; c++) {
+            Tile t{c * bgx, p * bgy, comb_extent(r.full_w, bgx, bC, c), comb_extent(r.full_h, bgy, bP, p), TileComb{}};
+            t.comb.gx = bgx; t.comb.sx = bC * bgx; t.comb.gy = bgy; t.comb.sy = bP * bgy;
+            if (t.w && t.h) tiles.push_back(t);
+        }
+    return tiles;
+}
+
 // Tile list, in claim order.  With a tile size from the caller: a uniform grid.  Chosen by the library: a base tile
 // so that every rank has ~24 tiles to steal from while a tile keeps enough paths to fill a launch (multiples of
 // the 32 x 16 pixel granule of the path order) — and, for several ranks, GUIDED scheduling: the first ~60 % of the
 // rows are cut into tiles of 2 x 2 base tiles, which run closer to the GPU's large-wave rate, and only the rest
 // into base tiles, which are what balances the ranks at the end of the frame (big units first, small units last).
-std::vector<Tile> make_tiles(const ptb_frame_req& r, int world) {
+// → the frame's tiles in claim order, and the number of tiles each rank keeps in flight (host threads / streams).
+std::vector<Tile> make_tiles(const ptb_frame_req& r, int world, int* workers_out = nullptr) {
     uint32_t tw = r.tile_w, th = r.tile_h;
     const bool chosen = (tw == 0 || th == 0);
+    int in_flight = r.tiles_in_flight ? (int)r.tiles_in_flight : (int)g_options.frame_tiles_in_flight;
+    in_flight = std::max(1, std::min(in_flight, MAX_IN_FLIGHT));
+    if (workers_out) *workers_out = in_flight;
+    if (chosen && ((world > 1 && g_options.frame_comb_tiles == 1) || g_options.frame_comb_tiles == 2)) {
+        // Comb tiles cost the same, so every stream gets the same number of them and size is free to choose: a tile
+        // of ~4 M paths runs close to the GPU's large-launch rate and 3+ of them in flight keep the SMs busy across
+        // the tiles' own tails (C2 over 8 GPUs: 28.4 / 28.8 / 29.7 ms per frame with 4 / 6 / 8 in flight).  A tile
+        // of more than 32 M paths is cut further (rounds), which lets a slow GPU shed work to the others.
+        const double share = double(r.full_w) * r.full_h * std::max<uint32_t>(r.spp, 1) / world; // paths per GPU
+        int k = in_flight;
+        if (!r.tiles_in_flight) k = (int)std::max(3.0, std::min(double(in_flight), std::floor(share / double(4 << 20) + 0.5)));
+        int64_t rounds = g_options.frame_comb_rounds;
+        if (rounds <= 0) rounds = std::max<int64_t>(1, std::min<int64_t>(64, (int64_t)std::ceil(share / k / double(32 << 20))));
+        std::vector<Tile> comb = make_comb_tiles(r, uint32_t(world) * uint32_t(k) * uint32_t(rounds));
+        if (!comb.empty()) {
+            if (workers_out) *workers_out = k;
+            return comb;
+        }
+    }
     if (chosen) {
         const uint64_t want = uint64_t(world) * 24;
         tw = 32;
@@ -359,27 +438,35 @@ std::vector<Tile> make_tiles(const ptb_frame_req& r, int world) {
         const uint32_t bw = std::min(2 * tw, r.full_w), bh = 2 * th;
         const uint32_t big_rows = uint32_t(uint64_t(r.full_h) * 6 / 10) / bh * bh;
         for (; y0 < big_rows; y0 += bh)
-            for (uint32_t x = 0; x < r.full_w; x += bw) tiles.push_back(Tile{x, y0, std::min(bw, r.full_w - x), bh});
+            for (uint32_t x = 0; x < r.full_w; x += bw) tiles.push_back(Tile{x, y0, std::min(bw, r.full_w - x), bh, TileComb{}});
     }
     for (uint32_t y = y0; y < r.full_h; y += th)
-        for (uint32_t x = 0; x < r.full_w; x += tw) tiles.push_back(Tile{x, y, std::min(tw, r.full_w - x), std::min(th, r.full_h - y)});
+        for (uint32_t x = 0; x < r.full_w; x += tw) tiles.push_back(Tile{x, y, std::min(tw, r.full_w - x), std::min(th, r.full_h - y), TileComb{}});
     return tiles;
 }
 
 } // namespace
 
-void frame_tiles(const ptb_frame_req& req, int world, uint32_t* xywh, uint64_t capacity, uint32_t* n_tiles) {
+void frame_tiles(const ptb_frame_req& req, int world, uint32_t* out, uint64_t capacity, uint32_t* n_tiles, bool with_comb) {
     if (req.full_w == 0 || req.full_h == 0 || world < 1) throw Error(PTB_E_INVALID, "empty frame or bad world size");
     if (!n_tiles) throw Error(PTB_E_INVALID, "n_tiles is NULL");
     const std::vector<Tile> tiles = make_tiles(req, world);
     *n_tiles = (uint32_t)tiles.size();
-    if (xywh) {
+    if (out) {
         if (capacity < tiles.size()) throw Error(PTB_E_INVALID, "capacity too small");
+        const size_t stride = with_comb ? 8 : 4;
         for (size_t i = 0; i < tiles.size(); i++) {
-            xywh[4 * i] = tiles[i].x0;
-            xywh[4 * i + 1] = tiles[i].y0;
-            xywh[4 * i + 2] = tiles[i].w;
-            xywh[4 * i + 3] = tiles[i].h;
+            uint32_t* o = out + stride * i;
+            o[0] = tiles[i].x0;
+            o[1] = tiles[i].y0;
+            o[2] = tiles[i].w;
+            o[3] = tiles[i].h;
+            if (with_comb) {
+                o[4] = tiles[i].comb.gx;
+                o[5] = tiles[i].comb.sx;
+                o[6] = tiles[i].comb.gy;
+                o[7] = tiles[i].comb.sy;
+            }
         }
     }
 }
@@ -556,13 +643,12 @@ void group_render_frame(ptb_group* g, const ptb_scene* scene, const ptb_frame_re
     PTB_CUDA(cudaSetDevice(g->device));
     GroupShared* sh = g->sh;
 
-    const std::vector<Tile> tiles = make_tiles(req, g->world);
+    int n_workers = 1;
+    const std::vector<Tile> tiles = make_tiles(req, g->world, &n_workers);
     ensure_frame(g, req.full_w, req.full_h);
     const uint64_t e = g->epoch++;
     const size_t npix = size_t(req.full_w) * req.full_h;
     float4* frame = g->frame_view + (e & 1u) * npix;
-    int n_workers = req.tiles_in_flight ? (int)req.tiles_in_flight : (int)g_options.frame_tiles_in_flight;
-    n_workers = std::max(1, std::min(n_workers, MAX_IN_FLIGHT));
     ensure_workers(g, n_workers);
 
     // post the job

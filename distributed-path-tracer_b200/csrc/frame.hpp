@@ -29,7 +29,7 @@ void group_render_frame(ptb_group* g, const ptb_scene* scene, const ptb_frame_re
 // the last rendered frame in device memory as this rank sees it (tests)
 const float4* group_frame_dev(const ptb_group* g);
 
-void frame_tiles(const ptb_frame_req& req, int world, uint32_t* xywh, uint64_t capacity, uint32_t* n_tiles);
+void frame_tiles(const ptb_frame_req& req, int world, uint32_t* out, uint64_t capacity, uint32_t* n_tiles, bool with_comb);
 
 ptb_ctx* ctx_create(int n_gpus, const int* devices);
 void ctx_destroy(ptb_ctx* c);

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256)
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (!valid) continue;
         const uint32_t k = base + __popc(mask & ((1u << lane) - 1u));
-        const uint32_t gx = g.x0 + x, gy = g.y0 + y;
+        const uint32_t gx = g.x0 + g.comb_x(x), gy = g.y0 + g.comb_y(y);
         const uint32_t sample = g.first_sample + s;
         float aax = 0.0f, aay = 0.0f;
         if (!(sample == 0 && rp.first_sample_unjittered)) {
@@ -181,7 +181,7 @@ __device__ __forceinline__ bool shade_path(const DScene& S, const WaveGeom& g, c
     path_to_sample_slot(g, st.p, s, q);
     uint32_t x, y;
     slot_to_pixel(g, q, x, y);
-    const uint32_t pixel_id = (g.y0 + y) * g.full_w + (g.x0 + x);
+    const uint32_t pixel_id = (g.y0 + g.comb_y(y)) * g.full_w + (g.x0 + g.comb_x(x));
     const uint32_t sample = g.first_sample + s;
     const Philox ph{rp.seed_lo, rp.seed_hi};
     const uint4 ra = ph(pixel_id, sample, event, 0u);
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         const uint32_t x = i % g.w, y = i / g.w;
         const uint32_t q = pixel_to_slot(g, x, y);
-        float4* out = dst + size_t(y) * pitch + x;
+        float4* out = dst + size_t(g.comb_y(y)) * pitch + g.comb_x(x);
         float4 px = fresh ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : *out;
         bool cl = (transparent && !fresh) ? (claimed[i] != 0) : false;
         for (uint32_t s = 0; s < g.wave_samples; s++) {

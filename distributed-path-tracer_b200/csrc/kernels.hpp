@@ -24,6 +24,12 @@ struct WaveGeom {
     uint32_t wave_samples;         // samples of every pixel in this wave
     uint32_t first_sample;         // global index of the wave's first sample
     uint32_t block_major;          // path order: 1 = the wave's samples of an 8x4 block adjacent, 0 = sample planes
+    // COMB tiles (frame.cu): the tile's columns / rows are granules of comb_gx / comb_gy pixels that lie comb_sx /
+    // comb_sy pixels apart in the frame (0: a plain rectangle).  Tile pixel (x, y) is frame pixel
+    // (x0 + comb_x(x), y0 + comb_y(y)); only ray generation, the RNG's pixel id and the accumulate store care.
+    uint32_t comb_gx, comb_sx, comb_gy, comb_sy;
+    __host__ __device__ uint32_t comb_x(uint32_t x) const { return comb_gx ? (x / comb_gx) * comb_sx + x % comb_gx : x; }
+    __host__ __device__ uint32_t comb_y(uint32_t y) const { return comb_gy ? (y / comb_gy) * comb_sy + y % comb_gy : y; }
 };
 
 struct RenderParams {

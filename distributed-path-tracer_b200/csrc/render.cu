@@ -173,13 +173,14 @@ void ensure_tile_buffers(Workspace& w, const TileSizing& z, uint32_t max_depth, 
 //   stats      non-null: counters are reset, the stream is synchronised at the end and the totals returned;
 //              null: nothing is reset or read (the frame driver reads the workspace's counters once per frame)
 void render_tile_locked(Workspace& w, const ptb_scene* s, const ptb_tile_req& req, const TileTarget& dst, cudaStream_t st,
-                        ptb_render_stats* stats) {
+                        ptb_render_stats* stats, const TileComb& comb = TileComb{}) {
     w.events();
 
     const TileSizing sizing = size_tile(req.w, req.h, req.spp);
     WaveGeom g = sizing.g;
     g.full_w = req.full_w; g.full_h = req.full_h;
     g.x0 = req.x0; g.y0 = req.y0;
+    g.comb_gx = comb.gx; g.comb_sx = comb.sx; g.comb_gy = comb.gy; g.comb_sy = comb.sy;
     const uint64_t wave_samples = sizing.wave_samples;
 
     RenderParams rp{};
@@ -345,12 +346,27 @@ void check_tile_req(const ptb_scene* s, const ptb_tile_req& req) {
 
 // ---- entry points used by the frame driver (frame.cu) -----------------------------------------------------------
 
-void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, float4* base, uint32_t pitch, cudaStream_t st) {
-    check_tile_req(s, req);
+void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, const TileComb& comb, float4* base, uint32_t pitch,
+                      cudaStream_t st) {
+    if (comb.gx || comb.gy) {
+        // the last pixel of the comb must lie inside the frame (check_tile_req knows rectangles only)
+        WaveGeom g{};
+        g.comb_gx = comb.gx; g.comb_sx = comb.sx; g.comb_gy = comb.gy; g.comb_sy = comb.sy;
+        if (!s) throw Error(PTB_E_INVALID, "scene is NULL");
+        if (req.w == 0 || req.h == 0 || (comb.gx && comb.sx < comb.gx) || (comb.gy && comb.sy < comb.gy) ||
+            uint64_t(req.x0) + g.comb_x(req.w - 1) >= req.full_w || uint64_t(req.y0) + g.comb_y(req.h - 1) >= req.full_h)
+            throw Error(PTB_E_INVALID, "comb tile exceeds the frame");
+        ptb_tile_req plain = req;
+        plain.x0 = plain.y0 = 0;
+        plain.w = plain.h = 1;
+        check_tile_req(s, plain);
+    } else {
+        check_tile_req(s, req);
+    }
     if (!base) throw Error(PTB_E_INVALID, "destination is NULL");
     Workspace& w = workspace(s->device, st);
     std::lock_guard<std::mutex> guard(w.lock);
-    render_tile_locked(w, s, req, TileTarget{base, pitch, nullptr}, st, nullptr);
+    render_tile_locked(w, s, req, TileTarget{base, pitch, nullptr}, st, nullptr, comb);
 }
 
 void reserve_tile_workspace(const ptb_scene* s, cudaStream_t st, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth) {

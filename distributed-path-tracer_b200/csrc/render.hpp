@@ -26,6 +26,8 @@ struct Options {
     int64_t time_stages = 0;            // CUDA-event pair around every extend / shade launch (perturbs the total)
     int64_t group_timeout_ms = 120000;  // multi-GPU: longest wait at a barrier / rendezvous before PTB_E_NCCL
     int64_t frame_tiles_in_flight = 8;  // multi-GPU frame: host threads (streams) per GPU
+    int64_t frame_comb_tiles = 1;       // library-chosen tiling: 1 = comb tiles (frame.cu) for several ranks, 2 = always (tests), 0 = never
+    int64_t frame_comb_rounds = 0;      // comb tiles per stream (0: as many as keep a tile under 32 M paths)
     int64_t frame_guided_tiles = 1;     // library-chosen tiling for several ranks: big tiles first, small tiles last
     int64_t frame_spin_wait = 0;        // workers wait for their tiles by spinning instead of sleeping on a blocking event
     int64_t frame_queue_depth = 1;      // tiles queued per stream (1: claim after the previous tile finished, 2: one ahead)
@@ -38,7 +40,13 @@ void render_tile_host(const ptb_scene* s, const ptb_tile_req& req, float* rgb_ou
                       ptb_render_stats* stats);
 // frame driver: one tile accumulated in place at `base` (pitch pixels per row, own or peer-mapped memory),
 // asynchronous on `st`; rays / paths / launches add up in the stream's workspace until they are read
-void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, float4* base, uint32_t pitch, cudaStream_t st);
+// comb: granule / stride in x and y (kernels.hpp: WaveGeom::comb_*), all 0 for a plain rectangle; req.w / req.h are
+// then the pixels the tile covers, req.x0 / req.y0 its first granule
+struct TileComb {
+    uint32_t gx = 0, sx = 0, gy = 0, sy = 0;
+};
+void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, const TileComb& comb, float4* base, uint32_t pitch,
+                      cudaStream_t st);
 // sizes the stream's workspace for w x h tiles before a frame starts (no allocation inside the frame)
 void reserve_tile_workspace(const ptb_scene* s, cudaStream_t st, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth);
 void stream_counters_reset(int device, cudaStream_t st);

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 3
+#define PTB_ABI_VERSION 4
 
 typedef enum ptb_status {
     PTB_OK = 0,
@@ -362,6 +362,15 @@ typedef struct ptb_frame_stats {
  * tile_w / tile_h in the request: a uniform row-major grid.  With 0: the library's choice — for several ranks big
  * tiles first and small tiles last (guided scheduling).  Call with xywh == NULL to obtain the count. */
 ptb_status ptb_frame_tiles(const ptb_frame_req* req, int world, uint32_t* xywh, uint64_t capacity, uint32_t* n_tiles);
+
+/* The same with the tiles' pixel layout: eight values per tile, (x0, y0, w, h, gx, sx, gy, sy).  For several ranks
+ * the library's choice is COMB tiles: tile pixel (x, y), 0 <= x < w, 0 <= y < h, is frame pixel
+ *   (x0 + (x / gx) * sx + x % gx,  y0 + (y / gy) * sy + y % gy)
+ * i.e. granules of gx x gy pixels that lie sx / sy pixels apart — every tile samples the whole image, so all tiles
+ * cost the same and each can be as large as a GPU's share of the frame divided by its streams (a frame cut into
+ * rectangles needs SMALL tiles to balance sky against terrain, and small launches are slow).  gx = gy = 0: a plain
+ * rectangle.  A frame's pixels never depend on the tiling (they are a function of seed, pixel and sample). */
+ptb_status ptb_frame_tile_layout(const ptb_frame_req* req, int world, uint32_t* layout, uint64_t capacity, uint32_t* n_tiles);
 
 /* One process per GPU (torchrun, MPI, ...): collective over `world` processes of ONE node that pass the same
  * `name` (a POSIX shared-memory object "/ptb_<name>": tile counters, barrier, IPC handle of the frame).

@@ -97,7 +97,16 @@ def main():
 
     if os.environ.get("SWEEP_SETTINGS"):
         # explicit list: [[tile_w, tile_h, streams, queue_depth, spin, rays_per_lane], ...]
-        for tw, th, streams, dq, spin, rpl in json.loads(os.environ["SWEEP_SETTINGS"]):
+        #            or {"tile": [w, h], "streams": n, "opts": {"frame_comb_tiles": 0, ...}, "host": false}
+        for item in json.loads(os.environ["SWEEP_SETTINGS"]):
+            if isinstance(item, dict):
+                for k, v in item.get("opts", {}).items():
+                    ptb.set_option(k, v)
+                if rank == 0:
+                    print(json.dumps({"opts": item.get("opts", {})}), flush=True)
+                run(tuple(item.get("tile", (0, 0))), item.get("streams", 0), 1, bool(item.get("host", False)))
+                continue
+            tw, th, streams, dq, spin, rpl = item
             run((tw, th), streams, dq, False, spin=spin, rpl=rpl)
         group.barrier()
         group.close()

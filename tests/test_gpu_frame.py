@@ -188,6 +188,49 @@ def test_context_frame_is_bit_identical_to_the_single_call(ptb, procedural, corn
         ctx.close()
 
 
+def test_comb_tiles_render_the_same_frame(ptb, procedural, cornell):
+    """The library's tiling for several ranks (comb tiles: every tile holds pixel granules spread over the whole frame,
+    include/ptb.h ptb_frame_tile_layout) forced onto whatever GPUs this box has: the tiles cover every pixel once, and
+    the frame is the single call's frame bit for bit — odd frame sizes, both integrators, transparent background."""
+    n = min(2, ptb.device_count())
+    ptb.set_option("frame_comb_tiles", 2)
+    try:
+        for (W, Hh, inflight) in [(96, 64, 3), (250, 131, 4), (333, 77, 2)]:
+            lay = ptb.frame_tile_layout(W, Hh, 4, n, tiles_in_flight=inflight)
+            assert len(lay) % (n * inflight) == 0 and (lay[:, 4] > 0).all() and (lay[:, 6] > 0).all()
+            cover = np.zeros((Hh, W), np.int32)
+            for row in lay:
+                xs, ys = ptb.tile_pixels(row)
+                cover[np.ix_(ys, xs)] += 1
+            assert (cover == 1).all()
+        ctx = ptb.Context(n)
+        try:
+            ctx.load_gltf(procedural.cornell_gltf_path())
+            for (W, Hh, spp, depth, integ, inflight) in [(96, 64, 8, 4, 0, 3), (250, 131, 5, 6, 1, 4), (333, 77, 3, 4, 0, 2)]:
+                want_rgb, want_a, st1 = cornell.render_tile(W, Hh, spp, depth, seed=5, integrator=integ)
+                frame, st = ctx.render_frame(W, Hh, spp, depth, seed=5, integrator=integ, tiles_in_flight=inflight)
+                assert st["n_tiles"] % (n * inflight) == 0
+                assert np.array_equal(H.bits(frame[..., :3]), H.bits(want_rgb)), (W, Hh)
+                assert np.array_equal(H.bits(frame[..., 3]), H.bits(want_a))
+                assert st["rays"] == st1["rays"] and st["paths"] == st1["paths"]
+        finally:
+            ctx.close()
+        d = procedural.heightfield_scene(16)
+        d.transparent_background = True
+        d.camera = (np.array([0, 3, 12], np.float32), d.camera[1], 0.9)
+        ctx = ptb.Context(n)
+        try:
+            ctx.set_scene(d)
+            with ptb.Scene.create(d) as s:
+                want_rgb, want_a, _ = s.render_tile(150, 90, 16, 4, seed=1)
+            frame, st = ctx.render_frame(150, 90, 16, 4, seed=1, tiles_in_flight=3)
+            assert np.array_equal(H.bits(frame[..., :3]), H.bits(want_rgb)) and np.array_equal(H.bits(frame[..., 3]), H.bits(want_a))
+        finally:
+            ctx.close()
+    finally:
+        ptb.set_option("frame_comb_tiles", 1)
+
+
 def test_context_transparent_background_and_worker_request(ptb, procedural, tmp_path):
     """Transparent-background claim logic through the frame driver, and the worker_info request over a context."""
     import json

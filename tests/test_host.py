@@ -218,6 +218,27 @@ def test_png_round_trip(ptb, tmp_path):
     assert np.array_equal(np.asarray(Image.open(path)), img)
 
 
+def test_frame_tilings_cover_every_pixel_once(ptb):
+    """ptb_frame_tile_layout: rectangles for one rank, comb tiles for several — every pixel in exactly one tile, comb
+    tiles equal to within 1 % (that is their point: all tiles cost the same, none is small)."""
+    for (W, Hh, world, k) in [(1920, 1080, 1, 8), (1920, 1080, 2, 8), (1920, 1080, 8, 8), (3840, 2160, 8, 8), (1921, 1083, 4, 6),
+                              (640, 480, 2, 4), (100, 37, 2, 8)]:
+        lay = ptb.frame_tile_layout(W, Hh, 64, world, tiles_in_flight=k)
+        cover = np.zeros((Hh, W), np.int32)
+        sizes = []
+        for row in lay:
+            xs, ys = ptb.tile_pixels(row)
+            cover[np.ix_(ys, xs)] += 1
+            sizes.append(len(xs) * len(ys))
+        assert (cover == 1).all(), (W, Hh, world)
+        auto = ptb.frame_tile_layout(W, Hh, 64, world)  # in flight chosen by the library: 3..8 tiles of ~4 M paths per GPU
+        assert [tuple(r[:4]) for r in auto.tolist()] == ptb.frame_tiles(W, Hh, 64, world)
+        if world > 1 and W >= 640:
+            assert len(lay) % (world * k) == 0 and (lay[:, 4] > 0).all()  # every stream of every rank: the same count
+            assert max(sizes) <= 1.02 * np.mean(sizes), (W, Hh, world, max(sizes) / np.mean(sizes))
+        # the plain list is the same tiles without their layout
+
+
 def test_tile_request_validation_needs_no_gpu(ptb):
     """NULL handles are refused before anything touches CUDA."""
     req = ptb.TileReq(8, 8, 0, 0, 8, 8, 1, 1, 1, 0, 0, 0, 0)
