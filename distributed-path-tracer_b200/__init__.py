@@ -153,7 +153,7 @@ EXPORTS = [
     "ptb_scene_blob", "ptb_scene_export_header", "ptb_scene_import", "ptb_scene_clone",
     "ptb_group_create", "ptb_group_destroy", "ptb_group_barrier", "ptb_group_render_frame",
     "ptb_ctx_create", "ptb_ctx_destroy", "ptb_ctx_set_scene", "ptb_ctx_load_gltf", "ptb_ctx_scene", "ptb_render_frame",
-    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host", "ptb_frame_tiles", "ptb_frame_tile_layout", "ptb_shadow_registers", "ptb_trace_occlusion",
+    "ptb_worker_run_ctx", "ptb_host_alloc", "ptb_host_free", "ptb_group_selftest_host", "ptb_frame_tiles", "ptb_frame_tile_layout", "ptb_shard_occlusion_dev", "ptb_shadow_registers", "ptb_trace_occlusion",
 ]
 
 _lib = None
@@ -265,6 +265,8 @@ def lib():
     L.ptb_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
     L.ptb_host_free.restype = None
     L.ptb_host_free.argtypes = [C.c_void_p]
+    L.ptb_shard_occlusion_dev.restype = st
+    L.ptb_shard_occlusion_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
     L.ptb_frame_tiles.restype = st
     L.ptb_frame_tiles.argtypes = [C.POINTER(FrameReq), C.c_int, u32p, C.c_uint64, u32p]
     L.ptb_frame_tile_layout.restype = st

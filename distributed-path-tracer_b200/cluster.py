@@ -396,6 +396,25 @@ class ShardMergeContext:
                                       C.c_void_p(hits_dev.data_ptr()), C.c_void_p(st)))
         return hits_dev
 
+    def occlusion(self, rays_dev):
+        """Shadow rays (float32 CUDA tensor [n, 6], identical on every rank) → uint8 CUDA tensor [n]: 1 where ANY
+        rank's shard occludes the ray.  The OR is done by the any-hit kernel itself, into every rank's buffer over
+        NVLink (``ptb_shard_occlusion_dev``); the key buffer doubles as the occlusion buffer."""
+        from . import lib, _check
+        torch, C = self.torch, self.C
+        n = int(rays_dev.shape[0])
+        if n > self.capacity * 8:
+            raise ValueError("more rays than the merge buffers hold")
+        rays_dev = rays_dev.contiguous()
+        occ = self.keys.view(torch.uint8)
+        occ[: (n + 3) // 4 * 4].zero_()
+        st = torch.cuda.current_stream().cuda_stream
+        self.h_keys.barrier(channel=0)       # everybody's buffer is zero before anybody ORs into it
+        _check(lib().ptb_shard_occlusion_dev(self.scene.h, C.c_void_p(rays_dev.data_ptr()), n, self.key_ptrs, self.world,
+                                             C.c_void_p(st)))
+        self.h_keys.barrier(channel=1)       # all ORs have landed
+        return occ[:n].clone()
+
 
 # ---------------------------------------------------------------------------------------------------------
 # Process-group glue for the frame driver of libptb (ptb_group): scene replication and the rendezvous name.

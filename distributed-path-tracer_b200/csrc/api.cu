@@ -210,6 +210,13 @@ ptb_status ptb_shard_trace_dev(const ptb_scene* shard, const float* origin_dir_d
     });
 }
 
+ptb_status ptb_shard_occlusion_dev(const ptb_scene* shard, const float* origin_dir_dev, uint64_t n, void* const* peer_occluded,
+                                   int world, void* stream) {
+    return guarded([&] {
+        ptb::shard_occlusion_dev(shard, origin_dir_dev, n, peer_occluded, world, static_cast<cudaStream_t>(stream));
+    });
+}
+
 ptb_status ptb_shard_publish_dev(const ptb_scene* shard, uint64_t n, const uint64_t* best_keys_dev,
                                  void* const* peer_payload, int world, void* stream) {
     return guarded([&] {

@@ -127,6 +127,11 @@ void launch_extend_lanes(const DScene& S, const float4* ray_o, const float4* ray
 void launch_extend_lanes_merge(const DScene& S, const float4* ray_o, const float4* ray_d, uint4* hits, float* t_out,
                                const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const MergeArgs* merge_dev,
                                const LaunchCfg& cfg, cudaStream_t st);
+// the shadow kernel with the geometry-shard exchange fused in: an occluded ray ORs its byte into every rank's
+// occlusion buffer (merge_dev->peers.keys[r] reinterpreted as bytes) over NVLink
+void launch_extend_anyhit_merge(const DScene& S, const float4* ray_o, const float4* ray_d, uint8_t* occluded,
+                                const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const MergeArgs* merge_dev,
+                                const LaunchCfg& cfg, cudaStream_t st);
 // the SHADOW kernel: the any-hit instantiation of the same kernel; occluded[k] = 1 when ray k hits anything
 void launch_extend_anyhit(const DScene& S, const float4* ray_o, const float4* ray_d, uint8_t* occluded,
                           const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,

@@ -649,6 +649,34 @@ void shard_trace_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, cons
     PTB_CUDA(cudaGetLastError());
 }
 
+void shard_occlusion_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, void* const* peer_occluded, int world,
+                         cudaStream_t st) {
+    check_rays(s, rays_dev, peer_occluded, n);
+    const ShardPeers peers = make_peers(peer_occluded, nullptr, world);
+    if (n == 0) return;
+    PTB_CUDA(cudaSetDevice(s->device));
+    Workspace& w = workspace(s->device, st);
+    std::lock_guard<std::mutex> guard(w.lock);
+    w.path[0][0].ensure(n * sizeof(float4));
+    w.path[0][1].ensure(n * sizeof(float4));
+    w.sh_occluded.ensure(n);
+    w.qcount.ensure((1 + QHEAD_STRIDE) * sizeof(uint32_t));
+    w.counters.ensure(sizeof(DeviceCounters));
+    MergeArgs args{peers, nullptr, nullptr};
+    w.io_b.ensure(sizeof(MergeArgs));
+    uint32_t* qc = (uint32_t*)w.qcount.p;
+    const uint32_t n32 = (uint32_t)n;
+    PTB_CUDA(cudaMemsetAsync(qc, 0, (1 + QHEAD_STRIDE) * sizeof(uint32_t), st));
+    PTB_CUDA(cudaMemcpyAsync(qc, &n32, sizeof(n32), cudaMemcpyHostToDevice, st));
+    PTB_CUDA(cudaMemcpyAsync(w.io_b.p, &args, sizeof(args), cudaMemcpyHostToDevice, st));
+    PTB_CUDA(cudaStreamSynchronize(st)); // n32 and args live on this stack frame
+    PTB_CUDA(cudaMemsetAsync(w.counters.p, 0, sizeof(DeviceCounters), st));
+    launch_prep_rays(rays_dev, n, (float4*)w.path[0][0].p, (float4*)w.path[0][1].p, st);
+    launch_extend_anyhit_merge(s->d, (const float4*)w.path[0][0].p, (const float4*)w.path[0][1].p, (uint8_t*)w.sh_occluded.p,
+                               &qc[0], &qc[1], (DeviceCounters*)w.counters.p, (const MergeArgs*)w.io_b.p, launch_cfg(s), st);
+    PTB_CUDA(cudaGetLastError());
+}
+
 void shard_publish_dev(const ptb_scene* s, uint64_t n, const uint64_t* best_keys_dev, void* const* peer_payload, int world,
                        cudaStream_t st) {
     check_rays(s, best_keys_dev, peer_payload, n);

@@ -59,6 +59,8 @@ void trace_rays_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, ptb_h
 void shard_reset_dev(uint64_t* keys_dev, uint64_t n, cudaStream_t st);
 void shard_trace_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, const uint32_t* instance_map_dev,
                      void* const* peer_keys, int world, cudaStream_t st);
+void shard_occlusion_dev(const ptb_scene* s, const float* rays_dev, uint64_t n, void* const* peer_occluded, int world,
+                         cudaStream_t st);
 void shard_publish_dev(const ptb_scene* s, uint64_t n, const uint64_t* best_keys_dev, void* const* peer_payload, int world,
                        cudaStream_t st);
 void shard_unpack_dev(const uint64_t* best_keys_dev, const void* payload_dev, uint64_t n, ptb_hit* hits_dev,

@@ -468,6 +468,15 @@ ptb_status ptb_shard_publish_dev(const ptb_scene* shard, uint64_t n, const uint6
 ptb_status ptb_shard_unpack_dev(const uint64_t* best_keys_dev, const void* payload_dev, uint64_t n, ptb_hit* hits_dev,
                                 void* stream);
 
+/* Geometry-sharded SHADOW query — intersection_worker.cpp:114-147: a shadow ray is lit only when NO worker's geometry
+ * occludes it.  Every rank traces the same rays against its shard with the any-hit kernel, and an occluded ray ORs
+ * its byte (1) into EVERY rank's occlusion buffer with a 32-bit atomic over NVLink, from inside the kernel.
+ * peer_occluded: HOST array of `world` device pointers (rank order) to buffers of n bytes rounded up to a multiple
+ * of 4, zeroed by their owners before anybody traces (memset + barrier); after a barrier behind the call every
+ * rank's buffer holds the merged answer, equal to ptb_trace_occlusion on the unsharded scene. */
+ptb_status ptb_shard_occlusion_dev(const ptb_scene* shard, const float* origin_dir_dev, uint64_t n, void* const* peer_occluded,
+                                   int world, void* stream);
+
 /* Host-only exercise of ptb_group's rendezvous, work-stealing counter and barrier (no CUDA): `frames` rounds in
  * which the `world` processes that pass the same `name` claim n_tiles tiles each (work_us microseconds of fake work
  * per tile); mine_out[e * n_tiles + i] = 1 where THIS rank claimed tile i of round e.  Over all ranks every tile of

@@ -60,6 +60,17 @@ def main():
     dist.barrier()
     dt = (time.perf_counter() - t0) / reps
     got = hits.cpu().numpy().view(ptb.HIT_DTYPE).reshape(-1)
+    # shadow query: any-hit against the shard, OR-merged into every rank's buffer from inside the kernel
+    occ = ctx.occlusion(rays)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        occ = ctx.occlusion(rays)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt_occ = (time.perf_counter() - t0) / reps
+    occ = occ.cpu().numpy().astype(bool)
     ok = True
     if rank == 0:
         with ptb.Scene.create(desc, device=torch.cuda.current_device()) as full:
@@ -72,9 +83,22 @@ def main():
         ok &= bool(np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)))
         ok &= bool(np.array_equal(got["bary"].view(np.uint32), want["bary"].view(np.uint32)))
         hit = want["instance"] != 0xFFFFFFFF
+        ok_occ = bool(np.array_equal(occ, hit))
         print(f"world {world}: sharded+merged == unsharded: {ok}; {hit.mean():.3f} of {n} rays hit; "
               f"sharded trace + peer-memory merge {dt*1e3:.2f} ms per call ({n/dt/1e6:.0f} Mrays/s), "
               f"unsharded host-API call {t_full*1e3:.2f} ms", flush=True)
+        print(f"world {world}: sharded shadow query == unsharded: {ok_occ}; any-hit trace + OR-merge over NVLink "
+              f"{dt_occ*1e3:.2f} ms per call ({n/dt_occ/1e6:.0f} Mrays/s)", flush=True)
+        ok &= ok_occ
+    else:
+        # every rank holds the merged answer: compare with rank 0's through an all-reduce below
+        pass
+    # all ranks must hold the SAME merged occlusion bytes
+    occ_dev = torch.from_numpy(occ.astype(np.int32)).cuda()
+    lo, hi = occ_dev.clone(), occ_dev.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok &= bool(torch.equal(lo, hi))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     shard.close()

@@ -318,6 +318,13 @@ def test_device_resident_trace_and_single_rank_shard_merge(ptb, cornell):
             ptb.set_option("extend_variant", 1)
         torch.cuda.synchronize()
         H.assert_hits_equal(out.cpu().numpy().view(ptb.HIT_DTYPE).reshape(-1), want, f"shard pipeline, variant {variant}")
+    # the sharded shadow query with one rank: the any-hit kernel ORs into its own buffer
+    occ = torch.zeros((n + 3) // 4 * 4, dtype=torch.uint8, device="cuda")
+    op = (C.c_void_p * 1)(occ.data_ptr())
+    assert L.ptb_shard_occlusion_dev(cornell.h, C.c_void_p(rays.data_ptr()), n, op, 1, st) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(occ[:n].cpu().numpy().astype(bool), cornell.trace_occlusion(od))
+    assert np.array_equal(occ[:n].cpu().numpy().astype(bool), want["instance"] != 0xFFFFFFFF)
 
 
 def test_peer_memory_shard_merge_on_two_gpus(ptb):
@@ -335,6 +342,7 @@ def test_peer_memory_shard_merge_on_two_gpus(ptb):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "sharded+merged == unsharded: True" in r.stdout
+    assert "sharded shadow query == unsharded: True" in r.stdout
 
 
 def test_instrumented_kernel_finds_no_bound_violation(ptb, procedural, cornell):
