@@ -274,12 +274,6 @@ def lib():
     L.ptb_group_selftest_host.restype = st
     L.ptb_group_selftest_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     _lib = L
-    # A/B runs of whole test suites / benches: PTB_OPTIONS="extend_defer=0,extend_setup_lanes=12"
-    for item in filter(None, os.environ.get("PTB_OPTIONS", "").split(",")):
-        name, _, value = item.partition("=")
-        st_ = L.ptb_set_option(name.strip().encode(), int(value))
-        if st_ != PTB_OK:
-            raise PtbError(st_, f"PTB_OPTIONS: {item!r}: " + L.ptb_last_error().decode("utf-8", "replace"))
     return L
 
 
