@@ -92,7 +92,8 @@ def _default_store():
 
 def render_frame(full_w: int, full_h: int, tiles: Sequence[Tile],
                  render_tile_fn: Callable[[Tile, "object", int], dict | None], frame, *, epoch: int = 0,
-                 static_assignment: bool = False, gather: bool = True, local_workers: int = 1):
+                 static_assignment: bool = False, gather: bool = True, local_workers: int = 1,
+                 sync_fn: Callable[[], None] | None = None):
     """Renders the tiles this rank claims into ``frame`` and gathers the full frame on rank 0.
 
     frame: a zero-initialised torch tensor [full_h, full_w, C] (device memory under NCCL, CPU under gloo);
@@ -101,7 +102,10 @@ def render_frame(full_w: int, full_h: int, tiles: Sequence[Tile],
            dict (its "rays" and "paths" entries are summed).  ``worker`` in [0, local_workers) identifies the
            host thread / CUDA stream: with local_workers > 1 several tiles of this rank are in flight at once
            (each on its own stream), which hides the tail of one tile's kernels behind the next tile's.
-    epoch: distinguishes successive frames in the store (a new counter key per frame).
+    epoch: distinguishes successive frames in the store (a new counter key per frame; the previous frame's key
+           is deleted once this frame has been reduced).
+    sync_fn: called before the gather: must make the CURRENT stream wait for whatever streams the workers rendered
+           on (the reduce is issued on the current stream).  Required with gather and local_workers > 1 on a device.
     Returns dict(rays, paths, tiles=[indices this rank rendered], seconds_render, seconds_gather).
     """
     dist = _dist()
@@ -147,8 +151,18 @@ def render_frame(full_w: int, full_h: int, tiles: Sequence[Tile],
         raise errors[0]
     t1 = time.perf_counter()
     if dist and gather and world > 1:
+        if sync_fn is not None:
+            sync_fn()
+        elif local_workers > 1 and getattr(frame, "is_cuda", False):
+            raise ValueError("render_frame(gather=True, local_workers > 1) on a CUDA frame needs sync_fn: the workers' "
+                             "streams must be joined to the current stream before the reduce reads their tiles")
         # disjoint tiles + zero elsewhere: SUM onto rank 0 is the gather of the framebuffer
         dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
+        if store is not None and rank == 0 and epoch > 0:
+            try:
+                store.delete_key(f"ptb_tiles_{epoch - 1}")  # everybody has left that frame (they are in this reduce)
+            except Exception:
+                pass  # not every store implements delete_key
     t2 = time.perf_counter()
     return dict(rays=totals["rays"], paths=totals["paths"], tiles=sorted(done), seconds_render=t1 - t0,
                 seconds_gather=t2 - t1)

@@ -120,27 +120,41 @@ struct Gltf {
         size_t count;
     };
 
+    // A JSON number that must be a byte count / element count: non-negative, integral, below 2^32 (a malformed or
+    // hostile file must produce an error, not undefined behaviour in the double -> size_t cast or a wrapped sum).
+    static size_t checked_size(const Json& o, const char* key, double fallback) {
+        const double v = o.get(key, fallback);
+        if (!(v >= 0.0) || v >= 4294967296.0 || v != std::floor(v)) throw Error(PTB_E_IO, std::string("glTF: bad ") + key);
+        return static_cast<size_t>(v);
+    }
+
     View accessor(long long idx) {
+        if (idx < 0 || static_cast<size_t>(idx) >= arr("accessors").size()) throw Error(PTB_E_IO, "glTF: accessor index out of range");
         const Json& a = arr("accessors").at(static_cast<size_t>(idx));
         View v{};
         v.ncomp = components_of(a.get("type", "SCALAR"));
         v.ctype = static_cast<int>(a.get("componentType", 5126));
         v.normalized = a.has("normalized") && a.at("normalized").b;
-        v.count = static_cast<size_t>(a.get("count", 0));
+        v.count = checked_size(a, "count", 0);
         const long long bv = a.index("bufferView");
         if (bv < 0) {
             v.data = nullptr;
             return v;
         }
+        if (static_cast<size_t>(bv) >= arr("bufferViews").size()) throw Error(PTB_E_IO, "glTF: bufferView index out of range");
         const Json& view = arr("bufferViews").at(static_cast<size_t>(bv));
-        const std::string& buf = buffer(static_cast<size_t>(view.get("buffer", 0)));
-        const size_t off = static_cast<size_t>(view.get("byteOffset", 0)) + static_cast<size_t>(a.get("byteOffset", 0));
+        const std::string& buf = buffer(checked_size(view, "buffer", 0));
+        const size_t view_off = checked_size(view, "byteOffset", 0), acc_off = checked_size(a, "byteOffset", 0);
         const size_t elem = static_cast<size_t>(v.ncomp) * component_size(v.ctype);
-        v.stride = static_cast<size_t>(view.get("byteStride", 0));
+        if (elem == 0) throw Error(PTB_E_IO, "glTF: bad accessor type / componentType");
+        v.stride = checked_size(view, "byteStride", 0);
         if (v.stride == 0) v.stride = elem;
-        if (v.count && off + (v.count - 1) * v.stride + elem > buf.size())
-            throw Error(PTB_E_IO, "glTF: accessor reads past the end of its buffer");
-        v.data = reinterpret_cast<const unsigned char*>(buf.data()) + off;
+        // the bytes the accessor touches, relative to the view: every term is below 2^32, so 64-bit sums cannot wrap
+        const uint64_t span = v.count ? uint64_t(acc_off) + uint64_t(v.count - 1) * v.stride + elem : 0;
+        const uint64_t view_len = view.has("byteLength") ? checked_size(view, "byteLength", 0) : uint64_t(buf.size());
+        if (span > view_len || uint64_t(view_off) + span > buf.size() || uint64_t(view_off) + view_len > buf.size())
+            throw Error(PTB_E_IO, "glTF: accessor reads past the end of its buffer view");
+        v.data = reinterpret_cast<const unsigned char*>(buf.data()) + view_off + acc_off;
         v.size = elem;
         return v;
     }
@@ -336,6 +350,7 @@ void load_gltf(const std::string& path, uint32_t camera_index, uint32_t sun_ligh
             const long long ii = prim.index("indices");
             if (ii < 0) throw Error(PTB_E_IO, "glTF: non-indexed primitives are not supported (nor by the reference)");
             const Gltf::View iv = g.accessor(ii);
+            if (!iv.data) throw Error(PTB_E_IO, "glTF: index accessor without a bufferView");
             m.indices.resize((iv.count / 3) * 3);
             for (size_t i = 0; i < m.indices.size(); i++) {
                 const unsigned char* p = iv.data + i * iv.stride;

@@ -209,6 +209,43 @@ def test_gltf_loader_errors(ptb, tmp_path):
     assert "camera" in str(e.value)  # renderer.cpp:73-74
 
 
+def test_gltf_loader_rejects_malformed_accessors(ptb, procedural, tmp_path):
+    """A malformed or hostile file must come back as PTB_E_IO, never as an out-of-bounds read: negative / fractional /
+    huge offsets, strides and counts, an accessor longer than its bufferView, an index accessor without a bufferView."""
+    import json
+    import shutil
+    src = os.path.dirname(procedural.cornell_gltf_path())
+    good = json.load(open(os.path.join(src, "cornell.gltf")))
+    shutil.copy(os.path.join(src, "cornell.bin"), tmp_path / "cornell.bin")
+    prim = good["meshes"][0]["primitives"][0]
+    pos_acc, idx_acc = prim["attributes"]["POSITION"], prim["indices"]
+
+    def broken(edit):
+        g = json.loads(json.dumps(good))
+        edit(g)
+        path = tmp_path / "m.gltf"
+        path.write_text(json.dumps(g))
+        with pytest.raises(ptb.PtbError) as e:
+            ptb.load_gltf_description(str(path))
+        assert e.value.status == ptb.PTB_E_IO, str(e.value)
+
+    ptb.load_gltf_description(os.path.join(src, "cornell.gltf"))  # the unedited file loads
+    broken(lambda g: g["accessors"][pos_acc].update(byteOffset=-16))
+    broken(lambda g: g["accessors"][pos_acc].update(byteOffset=1.5))
+    broken(lambda g: g["accessors"][pos_acc].update(count=2 ** 40))
+    broken(lambda g: g["accessors"][pos_acc].update(count=2 ** 31))  # (count - 1) * stride would wrap 32 bits
+    broken(lambda g: g["bufferViews"][g["accessors"][pos_acc]["bufferView"]].update(byteStride=2 ** 33))
+    broken(lambda g: g["bufferViews"][g["accessors"][pos_acc]["bufferView"]].update(byteOffset=2 ** 31))
+    broken(lambda g: g["bufferViews"][g["accessors"][pos_acc]["bufferView"]].update(byteLength=8))
+    broken(lambda g: g["bufferViews"][g["accessors"][idx_acc]["bufferView"]].update(buffer=7))
+    broken(lambda g: g["accessors"][idx_acc].pop("bufferView"))
+    broken(lambda g: prim_of(g).update(indices=10 ** 6))
+
+
+def prim_of(g):
+    return g["meshes"][0]["primitives"][0]
+
+
 def test_png_round_trip(ptb, tmp_path):
     from PIL import Image
     rng = np.random.default_rng(1)
