@@ -20,8 +20,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 INCLUDE = os.path.join(ROOT, "include")
-OUT = os.path.join(HERE, "libptb.so")
-OBJ = os.path.join(HERE, "build")
+# A/B builds: PTB_BUILD_TAG=x PTB_NVCC_EXTRA="-DPTB_FOO=1" → libptb_x.so (load it with PTB_LIB=.../libptb_x.so)
+TAG = os.environ.get("PTB_BUILD_TAG", "")
+OUT = os.path.join(HERE, "libptb" + ("_" + TAG if TAG else "") + ".so")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 
 CU_SOURCES = ["kernels.cu", "extend.cu", "scene.cu", "render.cu", "frame.cu", "api.cu"]
 # losing kernel variants kept for A/B measurements (option extend_variant = 0 / 3 / 4): PTB_BUILD_EXPERIMENTS=1
@@ -35,6 +37,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--fmad=false", "-prec-div=true"
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-I" + CSRC, "-I" + INCLUDE]
 if EXPERIMENTS:
     NVCC_FLAGS.append("-DPTB_BUILD_EXPERIMENTS=1")
+NVCC_FLAGS += os.environ.get("PTB_NVCC_EXTRA", "").split()
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-I" + CSRC, "-I" + INCLUDE]
 
 

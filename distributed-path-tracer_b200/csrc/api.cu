@@ -258,7 +258,7 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
 #endif
             ptb::g_options.extend_variant = value;
         } else if (n == "extend_steps") {
-            if (value < 2 || value > 6) throw ptb::Error(PTB_E_INVALID, "extend_steps must be 2..6");
+            if (value < 2 || value > 8) throw ptb::Error(PTB_E_INVALID, "extend_steps must be 2..8");
             ptb::g_options.extend_steps = value;
         } else if (n == "extend_setup_lanes") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_setup_lanes must be 1..32");
@@ -269,6 +269,12 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
         } else if (n == "frame_comb_rounds") {
             if (value < 0 || value > 64) throw ptb::Error(PTB_E_INVALID, "frame_comb_rounds must be 0..64");
             ptb::g_options.frame_comb_rounds = value;
+        } else if (n == "extend_dense_min2") {
+            if (value < 0 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_dense_min2 must be 0..32");
+            ptb::g_options.extend_dense_min2 = value;
+        } else if (n == "extend_dense") {
+            if (value < 0 || value > 1) throw ptb::Error(PTB_E_INVALID, "extend_dense must be 0 or 1");
+            ptb::g_options.extend_dense = value;
         } else if (n == "extend_defer") {
             if (value < 0 || value > 1) throw ptb::Error(PTB_E_INVALID, "extend_defer must be 0 or 1");
             ptb::g_options.extend_defer = value;
@@ -590,7 +596,7 @@ int ptb_extend_registers(void) {
     if (ptb::g_options.extend_variant == 4) return ptb::extend_ctx_regs_per_thread((int)ptb::g_options.extend_contexts);
     if (ptb::g_options.extend_variant == 0) return ptb::extend_regs_per_thread();
 #endif
-    return ptb::extend_lanes_regs_per_thread(ptb::g_options.extend_defer != 0);
+    return ptb::extend_lanes_regs_per_thread(ptb::g_options.extend_defer != 0, ptb::g_options.extend_dense != 0);
 }
 int ptb_shadow_registers(void) { return ptb::extend_anyhit_regs_per_thread(); }
 uint64_t ptb_selftest_division(uint64_t n, uint64_t seed) { return ptb::division_selftest(n, seed); }

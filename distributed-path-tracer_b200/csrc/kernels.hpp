@@ -65,6 +65,8 @@ struct LaunchCfg {
     int extend_sm_ranges;           // 1: every SM works through its own contiguous part of the queue first
     int extend_contexts;            // rays per lane of the context kernel (variant 4): 2..4
     int extend_rays_per_lane;       // blocks beyond ceil(n / (128 x this)) leave at once (0: all blocks stay)
+    int extend_dense_min2;          // DENSE: a 2nd test slot runs only with this many lanes still holding a leaf
+    int extend_dense;               // 1 (with extend_defer): leaf tests spread over the whole warp (extend.cu: DENSE)
 };
 
 // qcount[i] = number of live paths entering iteration i; qhead[i] = extend's work head for iteration i.
@@ -136,7 +138,9 @@ void launch_extend_anyhit_merge(const DScene& S, const float4* ray_o, const floa
 void launch_extend_anyhit(const DScene& S, const float4* ray_o, const float4* ray_d, uint8_t* occluded,
                           const uint32_t* n_ptr, uint32_t* head, DeviceCounters* counters, const LaunchCfg& cfg,
                           cudaStream_t st);
-int extend_lanes_regs_per_thread(bool defer);
+int extend_lanes_regs_per_thread(bool defer, bool dense);
+// the dense kernel's per-stream scratch, allocated ahead of a frame (a cudaMalloc inside it would stall every tile in flight)
+void extend_reserve_scratch(const LaunchCfg& cfg, cudaStream_t st);
 int extend_anyhit_regs_per_thread();
 
 // ---- experiments (csrc/experiments/, built only with PTB_BUILD_EXPERIMENTS=1; option extend_variant) ----

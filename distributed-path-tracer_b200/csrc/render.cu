@@ -109,6 +109,8 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.extend_tests = (int)g_options.extend_tests;
     c.extend_setup_lanes = (int)g_options.extend_setup_lanes;
     c.extend_defer = (int)g_options.extend_defer;
+    c.extend_dense = (int)g_options.extend_dense;
+    c.extend_dense_min2 = (int)g_options.extend_dense_min2;
     c.extend_sm_ranges = (int)g_options.extend_sm_ranges;
     c.extend_contexts = (int)g_options.extend_contexts;
     c.extend_rays_per_lane = (int)g_options.extend_rays_per_lane;
@@ -374,6 +376,7 @@ void reserve_tile_workspace(const ptb_scene* s, cudaStream_t st, uint32_t w, uin
     std::lock_guard<std::mutex> guard(ws.lock);
     ensure_tile_buffers(ws, size_tile(w, h, spp), max_depth, s->d.sun.enabled != 0, s->d.transparent_background != 0, w, h);
     ws.counters.ensure(sizeof(DeviceCounters));
+    extend_reserve_scratch(launch_cfg(s), st);
 }
 
 void stream_counters_reset(int device, cudaStream_t st) {

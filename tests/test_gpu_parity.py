@@ -30,23 +30,38 @@ def test_division_shortcut_is_exact(ptb):
     assert ptb.lib().ptb_selftest_division(1 << 28, 777) == 0
 
 
-VARIANTS = {"simple": (0, 2), "lanes": (1, 2), "coop": (3, 2), "ctx2": (4, 2), "ctx3": (4, 3),
-            "ctx4": (4, 4)}
+# (extend_variant, extend_contexts, other options).  "lanes" is the shipped kernel (deferred leaf tests spread over the
+# warp, dense entry pass at the refill); the next three are the same kernel with those designs switched off.
+VARIANTS = {"simple": (0, 2, {}), "lanes": (1, 2, {}),
+            "lanes_steps4": (1, 2, {"extend_steps": 4}),
+            "lanes_own_tests": (1, 2, {"extend_dense": 0}),
+            "lanes_own_tests_1": (1, 2, {"extend_dense": 0, "extend_tests": 1}),
+            "lanes_no_defer": (1, 2, {"extend_dense": 0, "extend_defer": 0}),
+            "coop": (3, 2, {}), "ctx2": (4, 2, {}), "ctx3": (4, 3, {}), "ctx4": (4, 4, {})}
+DEFAULTS = {"extend_variant": 1, "extend_contexts": 2, "extend_dense": 1, "extend_defer": 1, "extend_steps": 6,
+            "extend_tests": 2}
+
+
+def restore_default_kernel(ptb):
+    for k, v in DEFAULTS.items():
+        ptb.set_option(k, v)
+
 
 
 @pytest.fixture(params=list(VARIANTS), ids=list(VARIANTS))
 def extend_variant(ptb, request):
     """Every extend kernel the library carries (extend_variant / extend_contexts), default restored afterwards."""
-    variant, contexts = VARIANTS[request.param]
+    variant, contexts, options = VARIANTS[request.param]
     try:
         ptb.set_option("extend_variant", variant)
     except ptb.PtbError as e:  # the losing variants are only in a library built with PTB_BUILD_EXPERIMENTS=1
         assert variant != 1 and "PTB_BUILD_EXPERIMENTS" in str(e)
         pytest.skip("experiment kernels are not in the default build")
     ptb.set_option("extend_contexts", contexts)
+    for k, v in options.items():
+        ptb.set_option(k, v)
     yield request.param
-    ptb.set_option("extend_variant", 1)
-    ptb.set_option("extend_contexts", 2)
+    restore_default_kernel(ptb)
 
 
 def test_every_extend_kernel_against_goldens(cornell, extend_variant):
@@ -78,7 +93,7 @@ def test_every_extend_kernel_on_instances_and_a_deep_tree(ptb, procedural, exten
     od = np.concatenate([o, d], 1)
     with ptb.Scene.create(desc) as s:
         got = s.trace_rays(od)
-        ptb.set_option("extend_variant", 1)
+        restore_default_kernel(ptb)
         want = s.trace_rays(od)
     H.assert_hits_equal(got, want, f"variant {extend_variant} vs default")
     assert 0.05 < (want["instance"] != 0xFFFFFFFF).mean() < 0.98
