@@ -1032,10 +1032,13 @@ typedef struct {
 static void* render_rows(void* arg) {
     job_t* j = (job_t*)arg;
     rng_t g;
-    rng_seed(&g, j->seed * 0x100000001B3ull + (uint64_t)j->tid);
+    uint64_t rays = 0;
     for (;;) {
         uint32_t row = __sync_fetch_and_add(j->next_row, 1);
         if (row >= j->h) break;
+        /* one stream per image row (frame coordinates), not per thread: the image is a function of the seed alone,
+           whatever the thread count and however the rows fall to the threads */
+        rng_seed(&g, j->seed * 0x100000001B3ull + (uint64_t)(j->y0 + row));
         for (uint32_t col = 0; col < j->w; col++) {
             v3 color = V(0, 0, 0);
             float alpha = 0;
@@ -1059,8 +1062,9 @@ static void* render_rows(void* arg) {
             j->rgb[3 * i] = color.x; j->rgb[3 * i + 1] = color.y; j->rgb[3 * i + 2] = color.z;
             if (j->alpha) j->alpha[i] = alpha;
         }
+        rays += g.rays;
     }
-    j->rays = g.rays;
+    j->rays = rays;
     return NULL;
 }
 
