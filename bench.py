@@ -345,7 +345,7 @@ def run_ptb(args):
         if args.config == "c2":
             # C4: 3840x2160, 1024 spp, tile-sharded with work stealing; the frame return is part of the kernels
             c4_w, c4_h, c4_spp = 3840, 2160, args.c4_spp
-            timed(4, 1, 0, w=c4_w, h=c4_h)  # sizes the buffers
+            timed(4, 1, 0, w=c4_w, h=c4_h)  # maps the 4K frame on every rank (the buffers are sized by the frame itself)
             r = timed(c4_spp, 1, 0, w=c4_w, h=c4_h)
             if rank == 0:
                 extra["c4"] = {"workload": f"C4 {c4_w}x{c4_h} {c4_spp}spp depth{depth} over {world} GPUs",

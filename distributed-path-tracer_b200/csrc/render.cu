@@ -374,7 +374,15 @@ void render_tile_into(const ptb_scene* s, const ptb_tile_req& req, const TileCom
 void reserve_tile_workspace(const ptb_scene* s, cudaStream_t st, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth) {
     Workspace& ws = workspace(s->device, st);
     std::lock_guard<std::mutex> guard(ws.lock);
-    ensure_tile_buffers(ws, size_tile(w, h, spp), max_depth, s->d.sun.enabled != 0, s->d.transparent_background != 0, w, h);
+    // (w, h) is the frame's LARGEST tile, but a smaller tile may fit more samples into a wave and so come closer to
+    // wave_paths than the largest one does: size for the bound every tile obeys — a wave holds whole sample planes of
+    // at most wave_paths paths (or one plane if that is already larger), never more than spp planes.  A buffer that
+    // grows inside the frame costs a cudaFree, which waits for every tile in flight on the device.
+    TileSizing z = size_tile(w, h, spp);
+    const uint64_t planes = std::max<uint64_t>(1, std::max<uint32_t>(spp, 1));
+    z.cap = std::max<uint64_t>(z.cap, std::min<uint64_t>(std::max<uint64_t>((uint64_t)g_options.wave_paths, z.g.padded_pixels),
+                                                         planes * z.g.padded_pixels));
+    ensure_tile_buffers(ws, z, max_depth, s->d.sun.enabled != 0, s->d.transparent_background != 0, w, h);
     ws.counters.ensure(sizeof(DeviceCounters));
     extend_reserve_scratch(launch_cfg(s), st);
 }
