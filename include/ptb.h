@@ -489,11 +489,12 @@ ptb_status ptb_group_selftest_host(const char* name, int rank, int world, uint32
 int ptb_extend_registers(void);
 int ptb_shadow_registers(void);
 
-/* The extend kernel computes the split-plane distance (split - o) / d
- * (LIB/core/mesh.cpp:336-337) through a per-ray reciprocal and three FMAs, the
- * fast path of an IEEE division.  This runs n random operand pairs inside the
- * guarded exponent window through that shortcut on the GPU and returns how many
- * differ from the correctly rounded quotient (must be 0; ~0ull on a CUDA error). */
+/* The extend kernel's set-up computes the reciprocal ray direction of the slab tests
+ * (LIB/geometry/aabb.cpp:41-67) through a refined reciprocal and three FMAs, the
+ * fast path of an IEEE division (the split-plane distance (split - o) / d of a node
+ * step, LIB/core/mesh.cpp:336-337, is a plain IEEE division).  This runs n random operand
+ * pairs inside the guarded exponent window through that shortcut on the GPU and returns how
+ * many differ from the correctly rounded quotient (must be 0; ~0ull on a CUDA error). */
 uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
 
 /* ----------------------------------------------------------------- misc -- */
@@ -507,8 +508,13 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
  *                           3: warp-cooperative leaf tests; 4: several ray contexts per lane, traversal state in
  *                           shared memory
  *   "extend_contexts"       rays per lane of variant 4 (2..4)
- *   "extend_steps", "extend_tests"   tree levels (2 / 4 / 6: one, two or three double steps) / triangle tests (1..2)
+ *   "extend_steps", "extend_tests"   tree levels (2..8; instantiated: 4, 6 (default), 8) / triangle-test slots (1..2)
  *                           offered per loop iteration
+ *   "extend_defer"          1 (default): a lane registers a leaf and keeps descending while its triangles are tested
+ *   "extend_dense"          1 (default, needs extend_defer): a test slot spreads the registered leaves' triangles over
+ *                           all 32 lanes (a lane without a leaf tests a neighbour's triangle), and the first two
+ *                           instances a ray enters are resolved 32 wide when a warp refills its pool of rays
+ *   "extend_dense_min2"     lanes that must still hold a leaf for an iteration's second test slot to run (default 6)
  *   "extend_setup_lanes"    waiting lanes that trigger the set-up section (1..32, default 8)
  *   "extend_sm_ranges"      0/1: every SM starts on its own contiguous range of the ray queue (default 0)
  *   "path_order"            1: a wave's samples of one 8x4 pixel block are adjacent in the queue (default);
