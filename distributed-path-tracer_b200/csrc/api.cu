@@ -258,7 +258,7 @@ ptb_status ptb_set_option(const char* name, int64_t value) {
 #endif
             ptb::g_options.extend_variant = value;
         } else if (n == "extend_steps") {
-            if (value < 2 || value > 8) throw ptb::Error(PTB_E_INVALID, "extend_steps must be 2..8");
+            if (value != 0 && (value < 2 || value > 8)) throw ptb::Error(PTB_E_INVALID, "extend_steps must be 0 (by tree size) or 2..8");
             ptb::g_options.extend_steps = value;
         } else if (n == "extend_setup_lanes") {
             if (value < 1 || value > 32) throw ptb::Error(PTB_E_INVALID, "extend_setup_lanes must be 1..32");

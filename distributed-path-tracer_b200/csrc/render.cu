@@ -105,7 +105,10 @@ LaunchCfg launch_cfg(const ptb_scene* s) {
     c.shade_blocks_per_sm = (int)g_options.shade_blocks_per_sm;
     c.count_visits = g_options.count_visits != 0;
     c.extend_variant = (int)g_options.extend_variant;
-    c.extend_steps = (int)g_options.extend_steps;
+    // step slots per loop iteration: 6 pay on deep trees (C2: 58 node steps per ray, +1.3 %), and cost 5 % where a ray
+    // takes a handful of steps per mesh (Cornell: 3.5) — chosen by the average tree size unless the option says otherwise
+    c.extend_steps = g_options.extend_steps > 0 ? (int)g_options.extend_steps
+                                                : (s->d.n_pairs / std::max<uint32_t>(1u, s->info.n_meshes) >= 8192u ? 6 : 4);
     c.extend_tests = (int)g_options.extend_tests;
     c.extend_setup_lanes = (int)g_options.extend_setup_lanes;
     c.extend_defer = (int)g_options.extend_defer;

@@ -16,7 +16,7 @@ struct Options {
     int64_t extend_blocks_per_sm = 16;  // persistent extend grid = SMs x this
     int64_t shade_blocks_per_sm = 8;
     int64_t extend_variant = 1;         // 0: one thread per ray, 1: lane state machine with ray replacement
-    int64_t extend_steps = 6, extend_tests = 2; // work offered per main-loop iteration of the lane kernel
+    int64_t extend_steps = 0, extend_tests = 2; // work offered per main-loop iteration of the lane kernel (steps 0: by tree size)
     int64_t extend_setup_lanes = 8;             // lanes that must be waiting before the set-up section runs
     int64_t extend_dense_min2 = 6;              // DENSE: pending lanes the second test slot of an iteration asks for
     int64_t extend_dense = 1;                   // 1 (with extend_defer): leaf tests spread over the whole warp

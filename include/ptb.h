@@ -508,8 +508,8 @@ uint64_t ptb_selftest_division(uint64_t n, uint64_t seed);
  *                           3: warp-cooperative leaf tests; 4: several ray contexts per lane, traversal state in
  *                           shared memory
  *   "extend_contexts"       rays per lane of variant 4 (2..4)
- *   "extend_steps", "extend_tests"   tree levels (2..8; instantiated: 4, 6 (default), 8) / triangle-test slots (1..2)
- *                           offered per loop iteration
+ *   "extend_steps", "extend_tests"   tree levels (2..8; instantiated: 4, 6, 8; default 0 = 6 for scenes whose meshes
+ *                           average 8192+ node pairs, else 4) / triangle-test slots (1..2) offered per loop iteration
  *   "extend_defer"          1 (default): a lane registers a leaf and keeps descending while its triangles are tested
  *   "extend_dense"          1 (default, needs extend_defer): a test slot spreads the registered leaves' triangles over
  *                           all 32 lanes (a lane without a leaf tests a neighbour's triangle), and the first two

@@ -33,12 +33,12 @@ def test_division_shortcut_is_exact(ptb):
 # (extend_variant, extend_contexts, other options).  "lanes" is the shipped kernel (deferred leaf tests spread over the
 # warp, dense entry pass at the refill); the next three are the same kernel with those designs switched off.
 VARIANTS = {"simple": (0, 2, {}), "lanes": (1, 2, {}),
-            "lanes_steps4": (1, 2, {"extend_steps": 4}),
+            "lanes_steps4": (1, 2, {"extend_steps": 4}), "lanes_steps6": (1, 2, {"extend_steps": 6}),
             "lanes_own_tests": (1, 2, {"extend_dense": 0}),
             "lanes_own_tests_1": (1, 2, {"extend_dense": 0, "extend_tests": 1}),
             "lanes_no_defer": (1, 2, {"extend_dense": 0, "extend_defer": 0}),
             "coop": (3, 2, {}), "ctx2": (4, 2, {}), "ctx3": (4, 3, {}), "ctx4": (4, 4, {})}
-DEFAULTS = {"extend_variant": 1, "extend_contexts": 2, "extend_dense": 1, "extend_defer": 1, "extend_steps": 6,
+DEFAULTS = {"extend_variant": 1, "extend_contexts": 2, "extend_dense": 1, "extend_defer": 1, "extend_steps": 0,
             "extend_tests": 2}
 
 
