@@ -28,7 +28,9 @@
 
 #include <atomic>
 #include <chrono>
+#include <limits>
 #include <map>
+#include <optional>
 #include <thread>
 
 #include "ptb.h"
@@ -256,6 +258,185 @@ fvec4 trace_iter_app(const core::renderer& r, uint8_t initial_bounce, const geom
         bounce_remaining--;
     }
     return fvec4(accumulated_color, alpha);
+}
+
+// ---- the STAGED form of the app integrator, restated separately -----------------------------------------------------
+// The worker does not call trace_iter on its queue pipeline: a ray travels INTERSECT → [DIRECT_LIGHTING →] SHADING →
+// (INTERSECT ... | ACCUMULATE) as a models::cloud_ray (APP/models/cloud_ray.hpp:43-58).  This is that state machine for
+// one path and one worker (num_workers = 1: the min / or merges of intersection_worker.cpp:69-147 are identities),
+// written from the stage functions, NOT from trace_iter above — a second, independently restated oracle for row I-B:
+//   generate_rays                            APP/processors/worker/worker.cpp:117-146
+//   process_object_intersections             APP/processors/worker/intersection_worker.cpp:10-47
+//   process_object_intersection_results      intersection_worker.cpp:69-112   (which stage comes next)
+//   process_direct_lighting_intersections    intersection_worker.cpp:49-67
+//   process_shading                          APP/processors/worker/shading_worker.cpp:10-201
+// intersect_min_result (APP/scene/intersect.cpp:9-78) returns {hit, distance, position, tbn * normal map}: the same
+// closest hit and the same shading normal as intersect() + get_normal(), which is what the library exposes here.
+struct staged_ray { // the fields of models::cloud_ray the stages use
+    geometry::ray ray;
+    std::optional<geometry::ray> direct_light_ray;
+    float object_intersect_distance = 0;
+    bool direct_light_intersect_result = false;
+    fvec3 color = fvec3::zero;
+    float alpha = 0;
+    fvec3 scale = fvec3::one;
+    uint8_t bounce = 0;
+    int stage = 0; // 0 INTERSECT, 1 DIRECT_LIGHTING, 2 SHADING, 3 ACCUMULATE
+};
+
+static void stage_object_intersection(const core::renderer& r, staged_ray& ray) { // intersection_worker.cpp:21-40, 94-108
+    tl_rays++;
+    auto result = r.intersect(ray.ray);
+    ray.object_intersect_distance = result.hit ? 0.0f : std::numeric_limits<float>::max();
+    if (result.hit && r.sun_light) {
+        fvec3 direct_incoming = r.sun_light->get_global_transform().basis * fvec3::backward;
+        direct_incoming = util::rand_cone_vec(
+            core::rand(), math::cos(core::rand() * r.sun_light->get_component<scene::sun_light>()->angular_radius),
+            direct_incoming);
+        geometry::ray direct_ray(result.position + direct_incoming * math::epsilon, direct_incoming);
+        if (math::dot(result.get_normal(), direct_incoming) > 0)
+            ray.direct_light_ray = direct_ray;
+        else
+            ray.direct_light_ray = {};
+    }
+    // process_object_intersection_results with one worker: the only result is the best one
+    if (ray.object_intersect_distance == std::numeric_limits<float>::max())
+        ray.stage = 2;
+    else
+        ray.stage = ray.direct_light_ray.has_value() ? 1 : 2;
+}
+
+static void stage_direct_lighting(const core::renderer& r, staged_ray& ray) { // intersection_worker.cpp:58-66, 139-143
+    bool hit = false;
+    if (ray.direct_light_ray.has_value()) {
+        tl_rays++;
+        hit = r.intersect(ray.direct_light_ray.value()).hit;
+    }
+    ray.direct_light_intersect_result = hit;
+    ray.stage = 2;
+}
+
+static void stage_shading(const core::renderer& r, staged_ray& ray, uint8_t bounce_count) { // shading_worker.cpp:22-199
+    using namespace core;
+    geometry::ray& current_ray = ray.ray;
+    fvec3& accumulated_color = ray.color;
+    fvec3& throughput = ray.scale;
+    float& alpha = ray.alpha;
+
+    auto result = r.intersect(current_ray); // (the stage intersects again; not counted as a second ray of the path)
+    if (!result.hit) {
+        if (r.environment)
+            accumulated_color += throughput * (fvec3(r.environment->sample(equirectangular_proj(current_ray.get_dir()))) *
+                                               r.environment_factor);
+        else
+            accumulated_color += throughput * r.environment_factor;
+        alpha = r.transparent_background ? 0.0f : 1.0f;
+        ray.stage = 3;
+        return;
+    }
+    alpha = 1.0f;
+    fvec3 albedo = result.material->get_albedo(result.tex_coord);
+    float opacity = result.material->get_opacity(result.tex_coord);
+    float roughness = result.material->get_roughness(result.tex_coord);
+    float metallic = result.material->get_metallic(result.tex_coord);
+    fvec3 emissive = result.material->get_emissive(result.tex_coord) * 10;
+    float ior = result.material->ior;
+    accumulated_color += throughput * emissive;
+
+    if (!math::is_approx(opacity, 1) && core::rand() > opacity) {
+        current_ray = geometry::ray(result.position + current_ray.get_dir() * math::epsilon, current_ray.get_dir());
+        ray.stage = 0;
+        return;
+    }
+    fvec3 normal = result.get_normal();
+    fvec3 outcoming = -current_ray.get_dir();
+    if (math::dot(normal, outcoming) <= 0) {
+        ray.stage = 3;
+        return;
+    }
+    if (result.material->shadow_catcher && ray.bounce == bounce_count) { // shading_worker.cpp:71-105
+        bool in_shadow = true;
+        if (r.sun_light && ray.direct_light_ray.has_value()) {
+            fvec3 direct_incoming = ray.direct_light_ray.value().get_dir();
+            if (math::dot(normal, direct_incoming) > 0 && !ray.direct_light_intersect_result) in_shadow = false;
+        }
+        if (in_shadow) {
+            ray.color = fvec3::zero;
+            ray.alpha = 1;
+            ray.stage = 3;
+        } else {
+            current_ray = geometry::ray(result.position + current_ray.get_dir() * math::epsilon, current_ray.get_dir());
+            ray.stage = 0;
+        }
+        return;
+    }
+    roughness = math::max(roughness, 0.05F);
+    float specular_probability = core::pbr::fresnel(outcoming, core::reflect(-outcoming, normal), ior);
+    specular_probability = math::max(specular_probability, metallic);
+    bool specular_sample = core::rand() < specular_probability;
+
+    if (r.sun_light && ray.direct_light_ray.has_value()) { // shading_worker.cpp:112-146
+        fvec3 direct_incoming = ray.direct_light_ray.value().get_dir();
+        if (math::dot(normal, direct_incoming) > 0 && !ray.direct_light_intersect_result) {
+            float diffuse_pdf = pbr::pdf_diffuse(normal, direct_incoming);
+            fvec3 diffuse_brdf = diffuse_pdf * albedo;
+            float specular_pdf = pbr::pdf_specular(normal, outcoming, direct_incoming, roughness);
+            fvec3 specular_brdf(specular_pdf);
+            fvec3 fresnel = lerp(fvec3(0.04F), albedo, metallic);
+            fvec3 halfway = normalize(outcoming + direct_incoming);
+            fresnel = lerp(fresnel, fvec3::one, math::pow(1 - dot(outcoming, halfway), 5));
+            diffuse_brdf = lerp(diffuse_brdf, fvec3::zero, metallic);
+            fvec3 brdf = lerp(diffuse_brdf, specular_brdf, fresnel);
+            float pdf = lerp(1.0f, 1.0f, specular_probability);
+            fvec3 direct_in = r.sun_light->get_component<scene::sun_light>()->energy;
+            fvec3 direct_out = math::clamp(brdf * direct_in / math::max(pdf, math::epsilon), fvec3::zero, direct_in);
+            accumulated_color += throughput * direct_out;
+        }
+    }
+    fvec2 rand_val(core::rand(), core::rand());
+    fvec3 indirect_incoming = specular_sample ? pbr::importance_specular(rand_val, normal, outcoming, roughness)
+                                              : pbr::importance_diffuse(rand_val, normal, outcoming);
+    if (math::dot(normal, indirect_incoming) > 0) { // shading_worker.cpp:153-193
+        float diffuse_pdf = pbr::pdf_diffuse(normal, indirect_incoming);
+        fvec3 diffuse_brdf = diffuse_pdf * albedo;
+        float specular_pdf = pbr::pdf_specular(normal, outcoming, indirect_incoming, roughness);
+        fvec3 specular_brdf(specular_pdf);
+        fvec3 fresnel = lerp(fvec3(0.04F), albedo, metallic);
+        fvec3 halfway = normalize(outcoming + indirect_incoming);
+        fresnel = lerp(fresnel, fvec3::one, math::pow(1 - dot(outcoming, halfway), 5));
+        diffuse_brdf = lerp(diffuse_brdf, fvec3::zero, metallic);
+        fvec3 brdf = lerp(diffuse_brdf, specular_brdf, fresnel);
+        float pdf = lerp(diffuse_pdf, specular_pdf, specular_probability);
+        throughput *= brdf / math::max(pdf, math::epsilon);
+        throughput = math::clamp(throughput, fvec3::zero, fvec3(10.0f));
+        current_ray = geometry::ray(result.position + indirect_incoming * math::epsilon, indirect_incoming);
+        if (ray.bounce < bounce_count - 2) {
+            float p = math::max(throughput.x, math::max(throughput.y, throughput.z));
+            if (core::rand() > p) {
+                ray.stage = 3;
+                return;
+            }
+            throughput /= p;
+        }
+        ray.bounce -= 1;
+        ray.stage = ray.bounce > 0 ? 0 : 3;
+    } else {
+        ray.stage = 3;
+    }
+}
+
+fvec4 trace_staged_app(const core::renderer& r, uint8_t bounce_count, const geometry::ray& initial_ray) {
+    staged_ray ray;
+    ray.ray = initial_ray;
+    ray.bounce = bounce_count;
+    ray.stage = bounce_count > 0 ? 0 : 3;
+    ray.alpha = r.transparent_background ? 0.0f : 1.0f; // (cloud_ray leaves it uninitialised; only a 0-bounce request shows it)
+    while (ray.stage != 3) {
+        if (ray.stage == 0) stage_object_intersection(r, ray);
+        else if (ray.stage == 1) stage_direct_lighting(r, ray);
+        else stage_shading(r, ray, bounce_count);
+    }
+    return fvec4(ray.color, ray.alpha);
 }
 
 // Iterative equivalent of renderer::trace (LIB/core/renderer.cpp:437-643), used
@@ -775,6 +956,7 @@ void ref_count_visits(void* h, const float* od, uint64_t n, uint64_t* c6) {
 // mode 0: the reference's own recursive renderer::trace
 // mode 1: restated worker::trace_iter (APP_RR)
 // mode 2: iterative equivalent of mode 0 (counts rays)
+// mode 3: the staged form of the app integrator (shading_worker.cpp / intersection_worker.cpp), restated separately
 // rays_out: scene-level intersect calls (modes 1 and 2 only; 0 for mode 0).
 void ref_render_linear(void* h, uint32_t full_w, uint32_t full_h, uint32_t x0, uint32_t y0, uint32_t w,
                        uint32_t hgt, uint32_t spp, uint32_t depth, int mode, int first_sample_unjittered,
@@ -811,6 +993,7 @@ void ref_render_linear(void* h, uint32_t full_w, uint32_t full_h, uint32_t x0, u
                     geometry::ray ray = cam->get_ray(ndc, ratio);
                     fvec4 data = mode == 0   ? s->r.trace(depth, ray)
                                  : mode == 1 ? trace_iter_app(s->r, depth, ray)
+                                 : mode == 3 ? trace_staged_app(s->r, depth, ray)
                                              : trace_iter_lib(s->r, depth, ray);
                     if (transparent) { // renderer.cpp:374-393
                         if (data.w > 0.5 && !p.claimed) {

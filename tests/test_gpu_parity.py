@@ -449,6 +449,12 @@ def test_image_statistics_against_live_reference_sun_scene(ptb, reflib):
             se = diff.std(0) / np.sqrt(len(diff)) + 1e-4
             assert np.all(np.abs(diff.mean(0)) < 5 * se + 0.01 * np.abs(r_rgb.mean((0, 1)))), (diff.mean(0), se)
             assert abs(st["rays"] / st["paths"] - r_rays / (64 * 48 * 256)) < 0.05
+            if mode == 1:
+                # the worker's STAGED form of the app integrator (shading_worker.cpp:10-201, intersection_worker.cpp:
+                # 10-147), restated separately from trace_iter: a second, independent oracle for row I-B
+                s_rgb, _, _, _ = ref.render_linear(64, 48, 256, depth, mode=3)
+                ok, d2, se2 = H.block_mean_agreement(rgb, s_rgb)
+                assert ok, ("APP_RR vs the staged worker", d2, se2)
 
 
 @pytest.mark.parametrize("mode,ref_mode,depth", [(0, 0, 4), (1, 1, 6)])
