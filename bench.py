@@ -431,7 +431,7 @@ def run_ptb(args):
                        "scene_replication": "built once on rank 0; flattened blob broadcast over NCCL" if world > 1 else None,
                        "tiles": f"{n_tiles_main} tiles of {tile_desc}, stolen from one shared counter, "
                                 + (f"{args.streams} in flight per GPU" if args.streams else
-                                   (f"{n_tiles_main // world} per GPU (library's choice of tiles in flight: 3..8 of ~4 M paths)"
+                                   (f"{n_tiles_main // world} per GPU (library's choice of tiles in flight: 3..8 of ~5 M paths)"
                                     if tl[0][4] else "8 in flight per GPU")),
                        "tiles_per_rank": main["tiles_per_rank"],
                        "frame_return": "accumulate kernels store into rank 0's frame over NVLink (CUDA IPC), inside the timed region",

@@ -399,12 +399,13 @@ std::vector<Tile> make_tiles(const ptb_frame_req& r, int world, int* workers_out
     if (workers_out) *workers_out = in_flight;
     if (chosen && ((world > 1 && g_options.frame_comb_tiles == 1) || g_options.frame_comb_tiles == 2)) {
         // Comb tiles cost the same, so every stream gets the same number of them and size is free to choose: a tile
-        // of ~4 M paths runs close to the GPU's large-launch rate and 3+ of them in flight keep the SMs busy across
-        // the tiles' own tails (C2 over 8 GPUs: 28.4 / 28.8 / 29.7 ms per frame with 4 / 6 / 8 in flight).  A tile
+        // of ~5 M paths runs close to the GPU's large-launch rate and 3+ of them in flight keep the SMs busy across
+        // the tiles' own tails (C2 over 8 GPUs, v10 kernel: 26.9 / 27.6 / 27.3 ms per frame with 3 / 4 / 5 in flight;
+        // v9: 28.4 / 28.8 / 29.7 ms with 4 / 6 / 8).  A tile
         // of more than 32 M paths is cut further (rounds), which lets a slow GPU shed work to the others.
         const double share = double(r.full_w) * r.full_h * std::max<uint32_t>(r.spp, 1) / world; // paths per GPU
         int k = in_flight;
-        if (!r.tiles_in_flight) k = (int)std::max(3.0, std::min(double(in_flight), std::floor(share / double(4 << 20) + 0.5)));
+        if (!r.tiles_in_flight) k = (int)std::max(3.0, std::min(double(in_flight), std::floor(share / double(5 << 20) + 0.5)));
         int64_t rounds = g_options.frame_comb_rounds;
         if (rounds <= 0) rounds = std::max<int64_t>(1, std::min<int64_t>(64, (int64_t)std::ceil(share / k / double(32 << 20))));
         std::vector<Tile> comb = make_comb_tiles(r, uint32_t(world) * uint32_t(k) * uint32_t(rounds));
