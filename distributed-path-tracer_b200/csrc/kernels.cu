@@ -39,6 +39,10 @@ namespace ptb {
 namespace {
 
 constexpr int SHADE_THREADS = 128;
+#ifndef PTB_SHADE_MIN_BLOCKS
+#define PTB_SHADE_MIN_BLOCKS 8
+#endif
+constexpr int SHADE_MIN_BLOCKS = PTB_SHADE_MIN_BLOCKS;
 
 // flags packed in ray_d.w
 constexpr uint32_t F_BOUNCE_MASK = 0xFFu;  // bounces remaining
@@ -335,7 +339,7 @@ __device__ __forceinline__ bool shade_path(const DScene& S, const WaveGeom& g, c
 // Scenes with a sun: the shadow ray of every live path's shade event, compacted into the shadow queue.
 // shadow_slot[k] = the path's position in that queue (0xFFFFFFFF: this event casts none).
 template <bool APP_RR>
-__global__ void __launch_bounds__(SHADE_THREADS)
+__global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS)
     shadow_gen_kernel(DScene S, WaveGeom g, RenderParams rp, const float4* __restrict__ ray_o,
                       const float4* __restrict__ ray_d, const uint4* __restrict__ hits, float4* __restrict__ sh_o,
                       float4* __restrict__ sh_d, uint32_t* __restrict__ shadow_slot, const uint32_t* __restrict__ n_ptr,
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(SHADE_THREADS)
 }
 
 template <bool APP_RR, bool HAS_SUN>
-__global__ void __launch_bounds__(SHADE_THREADS)
+__global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS)
     shade_kernel(DScene S, WaveGeom g, RenderParams rp, PathBuffers in, const uint4* __restrict__ hits,
                  PathBuffers out, float4* __restrict__ sample_out, const uint32_t* __restrict__ n_ptr,
                  uint32_t* __restrict__ n_next, const uint32_t* __restrict__ shadow_slot,
@@ -597,38 +601,46 @@ void launch_raygen(const DScene& S, const WaveGeom& g, const RenderParams& rp, c
     raygen_kernel<<<grid_for(n, 256, cfg.sm_count * 8), 256, 0, st>>>(S, g, rp, out, sample_out, qcount0);
 }
 
+// Persistent grid-stride kernels (shade, shadow_gen): exactly the blocks that are resident at once, capped by the
+// option.  One block more than fits (8 requested, 7 resident at 72 registers) runs as a second wave on an almost empty
+// machine and the launch takes nearly twice as long as its work (shade: 27.9 against 27.0 ms per two C2 waves).
+template <typename F>
+int resident_grid(F fn, const LaunchCfg& cfg) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SHADE_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+    return cfg.sm_count * std::max(1, std::min(per_sm, cfg.shade_blocks_per_sm));
+}
+
 void launch_shadow_gen(const DScene& S, const WaveGeom& g, const RenderParams& rp, const float4* ray_o,
                        const float4* ray_d, const uint4* hits, float4* sh_o, float4* sh_d, uint32_t* shadow_slot,
                        const uint32_t* n_ptr, uint32_t* n_shadow, const LaunchCfg& cfg, cudaStream_t st) {
-    const int grid = cfg.sm_count * cfg.shade_blocks_per_sm;
     if (rp.integrator == 1)
-        shadow_gen_kernel<true><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, ray_o, ray_d, hits, sh_o, sh_d, shadow_slot, n_ptr,
-                                                                 n_shadow);
+        shadow_gen_kernel<true><<<resident_grid(shadow_gen_kernel<true>, cfg), SHADE_THREADS, 0, st>>>(
+            S, g, rp, ray_o, ray_d, hits, sh_o, sh_d, shadow_slot, n_ptr, n_shadow);
     else
-        shadow_gen_kernel<false><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, ray_o, ray_d, hits, sh_o, sh_d, shadow_slot, n_ptr,
-                                                                  n_shadow);
+        shadow_gen_kernel<false><<<resident_grid(shadow_gen_kernel<false>, cfg), SHADE_THREADS, 0, st>>>(
+            S, g, rp, ray_o, ray_d, hits, sh_o, sh_d, shadow_slot, n_ptr, n_shadow);
 }
 
 void launch_shade(const DScene& S, const WaveGeom& g, const RenderParams& rp, const PathBuffers& in,
                   const uint4* hits, const PathBuffers& out, float4* sample_out, const uint32_t* n_ptr,
                   uint32_t* n_next, const uint32_t* shadow_slot, const uint8_t* occluded, const LaunchCfg& cfg,
                   cudaStream_t st) {
-    const int grid = cfg.sm_count * cfg.shade_blocks_per_sm;
     const bool sun = S.sun.enabled != 0;
     if (rp.integrator == 1) {
         if (sun)
-            shade_kernel<true, true><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr, n_next,
-                                                                      shadow_slot, occluded);
+            shade_kernel<true, true><<<resident_grid(shade_kernel<true, true>, cfg), SHADE_THREADS, 0, st>>>(
+                S, g, rp, in, hits, out, sample_out, n_ptr, n_next, shadow_slot, occluded);
         else
-            shade_kernel<true, false><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr, n_next,
-                                                                       nullptr, nullptr);
+            shade_kernel<true, false><<<resident_grid(shade_kernel<true, false>, cfg), SHADE_THREADS, 0, st>>>(
+                S, g, rp, in, hits, out, sample_out, n_ptr, n_next, nullptr, nullptr);
     } else {
         if (sun)
-            shade_kernel<false, true><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr, n_next,
-                                                                       shadow_slot, occluded);
+            shade_kernel<false, true><<<resident_grid(shade_kernel<false, true>, cfg), SHADE_THREADS, 0, st>>>(
+                S, g, rp, in, hits, out, sample_out, n_ptr, n_next, shadow_slot, occluded);
         else
-            shade_kernel<false, false><<<grid, SHADE_THREADS, 0, st>>>(S, g, rp, in, hits, out, sample_out, n_ptr, n_next,
-                                                                        nullptr, nullptr);
+            shade_kernel<false, false><<<resident_grid(shade_kernel<false, false>, cfg), SHADE_THREADS, 0, st>>>(
+                S, g, rp, in, hits, out, sample_out, n_ptr, n_next, nullptr, nullptr);
     }
 }
 

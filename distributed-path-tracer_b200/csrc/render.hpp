@@ -14,7 +14,7 @@ struct Options {
     int64_t wave_paths = 8ll << 20;     // paths per wavefront (rounded to whole samples of the tile)
     int64_t count_visits = 0;           // instrumented extend kernel (node / leaf / triangle counters)
     int64_t extend_blocks_per_sm = 16;  // persistent extend grid = SMs x this
-    int64_t shade_blocks_per_sm = 8;
+    int64_t shade_blocks_per_sm = 32;
     int64_t extend_variant = 1;         // 0: one thread per ray, 1: lane state machine with ray replacement
     int64_t extend_steps = 0, extend_tests = 2; // work offered per main-loop iteration of the lane kernel (steps 0: by tree size)
     int64_t extend_setup_lanes = 8;             // lanes that must be waiting before the set-up section runs
