@@ -16,7 +16,8 @@ integrator = renderer::trace semantics.
     asks).  The scene is built once on rank 0 and its flattened blob broadcast over NCCL.  There is no
     collective in the data path: every rank's accumulate kernel stores its pixels into rank 0's frame over
     NVLink, so the frame return is INSIDE the timed region of `value`.  The weak-scaling figure (64 spp per
-    GPU) and BASELINE's C4 (3840x2160, 1024 spp) ride along as extra objects `weak` and `c4`;
+    GPU), BASELINE's C4 (3840x2160, 1024 spp) and C5 (49 instances of the 1 M-triangle mesh, 1080p x 64 spp) ride along
+    as extra objects `weak`, `c4` and `c5`;
     `--scaling weak` swaps the roles.
 `value` is timed with CUDA events on the library's streams (first tile start to last tile end, slowest rank)
 with the scene resident in HBM, barrier + synchronize on both sides.  `e2e` is host wall-clock around the
@@ -284,8 +285,10 @@ def run_ptb(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    leg = {"scene": scene}  # the scene the frames below render (the C5 leg swaps it)
+
     def frame(seed, spp, to_host, w=full_w, h=full_h):
-        return group.render_frame(scene, w, h, spp, depth, out=(pinned.data_ptr() if (to_host and rank == 0) else None),
+        return group.render_frame(leg["scene"], w, h, spp, depth, out=(pinned.data_ptr() if (to_host and rank == 0) else None),
                                   seed=seed, integrator=integ, tile=tile, tiles_in_flight=args.streams,
                                   output=ptb.OUT_RGBA32F if to_host else ptb.OUT_NONE)
 
@@ -352,6 +355,26 @@ def run_ptb(args):
                                "value": r["value"], "unit": "Mrays/s", "s_per_frame": r["ms_per_step"] * 1e-3,
                                "wall_s_per_frame": r["wall_ms_per_step"] * 1e-3, "n_tiles": r["n_tiles"],
                                "tiles_per_rank": r["tiles_per_rank"], "paths": r["paths"]}
+
+        if args.config == "c2" and not args.no_c5_leg:
+            # C5 (BASELINE configs[4]): 49 instances of the C2 mesh + the lights, 1080p x 64 spp, scene replicated like
+            # the main one (built once on rank 0, blob broadcast), the same frame driver
+            t0 = time.perf_counter()
+            scene5 = ptb.Scene.create(build_description("c5", args.n_grid), device_index) if rank == 0 else None
+            scene5 = cluster.replicate_scene(scene5, device_index)
+            t_scene5 = time.perf_counter() - t0
+            leg["scene"] = scene5
+            try:
+                r = timed(spp0, max(2, min(args.steps, 5)), 2)
+            finally:
+                leg["scene"] = scene
+            if rank == 0:
+                extra["c5"] = {"workload": f"{CONFIGS['c5'][0]} over {world} GPUs", "value": r["value"], "unit": "Mrays/s",
+                               "ms_per_step": r["ms_per_step"], "frames_per_s": 1e3 / r["ms_per_step"],
+                               "instances": int(scene5.info()["n_instances"]), "scene_build_and_replicate_s": t_scene5,
+                               "tiles_per_rank": r["tiles_per_rank"]}
+            barrier()
+            scene5.close()
 
     # ---- roofline of the dominant kernel (extend): separate, untimed-for-`value` passes on rank 0
     hbm_peak, peak_src = load_peaks()
@@ -614,7 +637,8 @@ def main():
     ap.add_argument("--tile", type=int, nargs=2, default=[0, 0], metavar=("W", "H"), help="tile size (0 0: library's choice)")
     ap.add_argument("--queue-depth", type=int, default=1, help="tiles queued per stream (1 or 2)")
     ap.add_argument("--c4-spp", type=int, default=1024, help="samples of the C4 leg (3840x2160) at N > 1")
-    ap.add_argument("--no-extra-legs", action="store_true", help="skip the weak-scaling / C4 legs at N > 1")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the weak-scaling / C4 / C5 legs at N > 1")
+    ap.add_argument("--no-c5-leg", action="store_true", help="skip the C5 (49-instance scene) leg at N > 1")
     ap.add_argument("--n-grid", type=int, default=707, help="heightfield grid (707 → 999 698 triangles)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
     ap.add_argument("--tiles-per-gpu", type=int, default=32,
