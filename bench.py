@@ -17,7 +17,7 @@ integrator = renderer::trace semantics.
     collective in the data path: every rank's accumulate kernel stores its pixels into rank 0's frame over
     NVLink, so the frame return is INSIDE the timed region of `value`.  The weak-scaling figure (64 spp per
     GPU), BASELINE's C4 (3840x2160, 1024 spp) and C5 (49 instances of the 1 M-triangle mesh, 1080p x 64 spp) ride along
-    as extra objects `weak`, `c4` and `c5`;
+    as extra objects `weak`, `c4` and `c5`; at N = 1 the Cornell-box configurations C1 and C3 do (`c1`, `c3`);
     `--scaling weak` swaps the roles.
 `value` is timed with CUDA events on the library's streams (first tile start to last tile end, slowest rank)
 with the scene resident in HBM, barrier + synchronize on both sides.  `e2e` is host wall-clock around the
@@ -285,11 +285,12 @@ def run_ptb(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    leg = {"scene": scene}  # the scene the frames below render (the C5 leg swaps it)
+    leg = {"scene": scene, "depth": depth, "integ": integ}  # what the frames below render (the extra legs swap it)
 
     def frame(seed, spp, to_host, w=full_w, h=full_h):
-        return group.render_frame(leg["scene"], w, h, spp, depth, out=(pinned.data_ptr() if (to_host and rank == 0) else None),
-                                  seed=seed, integrator=integ, tile=tile, tiles_in_flight=args.streams,
+        return group.render_frame(leg["scene"], w, h, spp, leg["depth"],
+                                  out=(pinned.data_ptr() if (to_host and rank == 0) else None), seed=seed,
+                                  integrator=leg["integ"], tile=tile, tiles_in_flight=args.streams,
                                   output=ptb.OUT_RGBA32F if to_host else ptb.OUT_NONE)
 
     def timed(spp, steps, warmup, to_host=False, w=full_w, h=full_h):
@@ -375,6 +376,21 @@ def run_ptb(args):
                                "tiles_per_rank": r["tiles_per_rank"]}
             barrier()
             scene5.close()
+
+    if world == 1 and args.config == "c2" and not args.no_extra_legs:
+        # the reference's own CPU-runnable case and the indirect-lighting case (BASELINE configs[0] and [2]: the bundled
+        # Cornell box; C3 with worker::trace_iter's Russian roulette at depth 16) ride along on one GPU
+        for name in ("c1", "c3"):
+            _, w_, h_, spp_, depth_, integ_ = CONFIGS[name]
+            sc = ptb.Scene.create(build_description(name, args.n_grid), device_index)
+            leg.update(scene=sc, depth=depth_, integ=integ_)
+            try:
+                r = timed(spp_, 3, 2, w=w_, h=h_)
+            finally:
+                leg.update(scene=scene, depth=depth, integ=integ)
+            extra[name] = {"workload": CONFIGS[name][0], "value": r["value"], "unit": "Mrays/s",
+                           "ms_per_step": r["ms_per_step"], "rays_per_path": r["rays"] / max(1, r["paths"])}
+            sc.close()
 
     # ---- roofline of the dominant kernel (extend): separate, untimed-for-`value` passes on rank 0
     hbm_peak, peak_src = load_peaks()
